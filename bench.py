@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- coordinate-ascent NDCG@10 evaluations/s on the 1M x 136 x 30k-query synthetic
+DenseDataset (BASELINE.json configs[1]; configs[2] when --gpus > 1: the same dataset sharded
+by query, one NCCL all-reduce of the metric sums per group of candidates).
+
+One STEP = one coordinate-ascent line search for each of the 8 restarts
+(coordinate_ascent.rs:131-177): group A (direction 0 + direction -1, 26 candidate weight
+vectors per restart) and group B (direction +1, 25 per restart) = 408 evaluate_mean
+equivalents (evaluators.rs:173-184), two calls of fr_dev_eval_coord_sweeps.  Every candidate is
+a full evaluation: all N documents scored with the reference's left-to-right f64 dot product,
+ranked inside their query, NDCG@10 per query, mean over queries.
+
+  value      evaluations/s with the dataset resident in HBM (device-timed, CUDA events on the
+             library's stream, max over ranks)
+  e2e        the same metric through the reference-facing C ABI with HOST buffers:
+             make_dense_dataset_f32_f64_i64 + train_model (CA, 8 restarts, to convergence);
+             the upload of X/y/qid is inside the timed region, evaluations counted are the
+             ones the reference's control flow consumes
+  roofline   dominant kernel (coord_sweep_kernel) vs the measured HBM copy bandwidth
+  cpu_baseline / --impl reference
+             the CPU oracle (C restatement of the reference; the Rust reference cannot be
+             built in this image) on the host cores, one thread per restart as the reference
+             does (coordinate_ascent.rs:216), on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_DOCS = 1_000_000
+N_FEAT = 136
+N_QUERIES = 30_000
+N_RESTARTS = 8
+T_ITERS = 25
+DEPTH = 10
+METRIC = "CA NDCG@10 evaluations/sec on 1M x 136 DenseDataset"
+UNIT = "evals/s"
+WORKLOAD = "synthetic 1M docs x 136 features x 30k queries, coordinate_ascent 8 restarts, ndcg@10"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_data(n=N_DOCS, d=N_FEAT, q=N_QUERIES):
+    from tests.helpers import synth
+
+    t = time.time()
+    X, y, qid = synth(n, d, q)
+    log("[bench] synthetic data %dx%d, %d queries in %.1fs" % (n, d, len(np.unique(qid)), time.time() - t))
+    return X, y, qid
+
+
+def line_search_candidates(orig: float, direction: int, step_base=0.05, step_scale=2.0, iters=T_ITERS):
+    """coordinate_ascent.rs:145-171"""
+    step = step_base * direction
+    if orig != 0.0 and abs(step) > 0.5 * abs(orig):
+        step = step_base * abs(orig) * direction
+    total = step
+    if direction == 0:
+        iters, total = 1, -orig
+    out = []
+    for _ in range(iters):
+        out.append(orig + total)
+        step *= step_scale
+        total += step
+    return out
+
+
+def step_inputs(step: int, d: int):
+    """Deterministic base weights (L1-normalised as CA does) and the feature each restart probes."""
+    rng = np.random.default_rng(1000 + step)
+    base = rng.uniform(-1.0, 1.0, size=(N_RESTARTS, d))
+    base /= np.abs(base).sum(axis=1, keepdims=True)
+    fids = [int((step * N_RESTARTS + r * 17) % d) for r in range(N_RESTARTS)]
+    group_a = [line_search_candidates(base[r, fids[r]], 0) + line_search_candidates(base[r, fids[r]], -1)
+               for r in range(N_RESTARTS)]
+    group_b = [line_search_candidates(base[r, fids[r]], +1) for r in range(N_RESTARTS)]
+    return base, fids, group_a, group_b
+
+
+EVALS_PER_STEP = N_RESTARTS * (1 + 2 * T_ITERS)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.gpu = gpu_index
+        self.path = os.path.join(ROOT, "gpurun_out", "clocks_rank%d.csv" % gpu_index)
+
+    def start(self):
+        try:
+            os.makedirs(os.path.dirname(self.path), exist_ok=True)
+            self.fp = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.fp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fp.close()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                   "power_w_max": float(max(power)), "samples": len(sm)}
+        return out
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_evals_per_sec(X, y, qid, evals_per_thread: int, threads: int = N_RESTARTS):
+    """`threads` workers (one per restart, as rayon does in the reference), each running
+    `evals_per_thread` full evaluate_mean equivalents with the C oracle."""
+    from oracle import oracle as orc
+    from tests.helpers import oracle_dataset
+
+    ods = oracle_dataset(orc, X, y, qid)
+    d = X.shape[1]
+
+    def work(r):
+        rng = np.random.default_rng(77 + r)
+        for _ in range(evals_per_thread):
+            w = rng.uniform(-1, 1, size=d)
+            per_query = orc.evaluate_scores(ods, orc.score_linear(X, w), "ndcg@%d" % DEPTH)
+            orc.mean(per_query)
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return threads * evals_per_thread / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    X, y, qid = make_data()
+    threads = min(N_RESTARTS, os.cpu_count() or 1)
+    for _ in range(args.warmup):
+        cpu_evals_per_sec(X, y, qid, 1, threads)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        v, dt = cpu_evals_per_sec(X, y, qid, 1, threads)
+        t_total += dt
+        n_total += threads
+    value = n_total / t_total
+    sample = "%d steps x %d threads x 1 full evaluate_mean (1M docs) each" % (args.steps, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "C restatement of the Rust reference (oracle/), not the Rust build"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import fastrank_b200 as fr
+    from fastrank_b200 import dist as frdist
+    from fastrank_b200._native import lib
+    from fastrank_b200.kernels import DevDataset, dense_query_index
+
+    if lib.fr_dev_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; fastrank_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = frdist.init_communicator(rank, world, local_rank, install_default=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    X, y, qid = make_data()
+    if world > 1:
+        rows = frdist.shard_rows(qid, rank, world)
+        Xl, yl, ql = np.ascontiguousarray(X[rows]), np.ascontiguousarray(y[rows]), np.ascontiguousarray(qid[rows])
+    else:
+        Xl, yl, ql = X, y, qid
+    n_local, d = Xl.shape
+    qidx, nq_local = dense_query_index(ql)
+
+    # ---- value: dataset resident in HBM ----------------------------------------------------
+    dev = DevDataset(Xl, yl.astype(np.float32), qidx, nq_local, device=local_rank)
+    plan = dev.plan(0, DEPTH)
+    if comm is not None:
+        if lib.fr_dev_plan_set_comm(plan.ptr, comm.ptr):
+            raise RuntimeError("fr_dev_plan_set_comm failed")
+
+    def one_step(s):
+        base, fids, ga, gb = step_inputs(s, d)
+        plan.coord_sweeps(base, fids, ga)
+        plan.coord_sweeps(base, fids, gb)
+
+    for s in range(args.warmup):
+        one_step(s)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = int(lib.fr_dev_kernel_launches())
+    dev.profile(True)
+    dev.profile_read(reset=True)
+    sampler.start()
+    dev.timer_start()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        one_step(args.warmup + s)
+    ms = dev.timer_stop()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
+    clocks = sampler.stop()
+    n_kern, kern_ms = dev.profile_read(reset=True)
+    dev.profile(False)
+    launches = int(lib.fr_dev_kernel_launches()) - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = EVALS_PER_STEP * args.steps / (ms / 1e3)
+
+    # roofline of the dominant kernel: one launch = N_RESTARTS sweeps over this rank's shard
+    per_sweep_bytes = n_local * d * 4 + n_local * 4 + (nq_local + 1) * 4 + 26 * d * 8 + 26 * 8
+    bytes_per_launch = N_RESTARTS * per_sweep_bytes
+    avg_launch_ms = kern_ms / max(n_kern, 1)
+    achieved = bytes_per_launch / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else 0.0
+    peak, peak_src = measured_peak_gbs()
+    traffic = recorded_traffic()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                "kernel": "coord_sweep_kernel<26,128>", "launches_timed": n_kern,
+                "avg_launch_ms": avg_launch_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "kernel_share_of_step": kern_ms / ms if ms > 0 else None, "peak_source": peak_src,
+                "note": "kernel is FP64-pipe bound (exact f64 dot in reference order), not HBM bound; see DESIGN.md"}
+    plan.close()
+    dev.close()
+
+    # ---- e2e: reference-facing C ABI with host buffers -------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    ds = fr.CDataset.from_numpy(Xl, yl, ql)
+    req = fr.TrainRequest.coordinate_ascent()
+    req.measure = "ndcg@%d" % DEPTH
+    req.params.num_restarts = N_RESTARTS
+    req.params.seed = 42
+    req.params.quiet = True
+    model = ds.train_model(req)
+    final = ds.evaluate_mean(model, req.measure)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    stats = fr.query_json("last_train_stats")
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d_total = Xl.nbytes + yl.nbytes + ql.nbytes + stats["sweeps"] * (d * 8 + 26 * 8 + 8)
+    d2h_total = stats["sweeps"] * 26 * 8
+    e2e = {"value": stats["evals_consumed"] / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": h2d_total / max(stats["global_steps"], 1),
+           "d2h_bytes_per_step": d2h_total / max(stats["global_steps"], 1),
+           "seconds": e2e_s, "evals_consumed": stats["evals_consumed"], "evals_computed": stats["evals_computed"],
+           "global_steps": stats["global_steps"], "final_train_ndcg10": final,
+           "what": "from_numpy + train_model(CA, 8 restarts, seed 42, to convergence) + evaluate through the C ABI"}
+    del ds, model
+
+    # ---- CPU baseline on the host cores (rank 0, single-GPU run only) -----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = min(N_RESTARTS, os.cpu_count() or 1)
+        per_thread = args.cpu_evals_per_thread
+        v, dt = cpu_evals_per_sec(X, y, qid, per_thread, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d threads x %d full evaluate_mean (1M docs, ndcg@10) with the C oracle, %.1fs" % (threads, per_thread, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "evals_per_step": EVALS_PER_STEP,
+                       "l2": "inputs (544 MB feature matrix per sweep) larger than the 126 MB L2",
+                       "parallelism": "query-sharded x%d" % world if world > 1 else "single GPU",
+                       "wall_ms_per_step": wall_ms / max(args.steps, 1)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-evals-per-thread", type=int, default=4)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

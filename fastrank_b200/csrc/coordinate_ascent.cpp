@@ -1,0 +1,246 @@
+// coordinate_ascent.cpp -- the coordinate-ascent learner (coordinate_ascent.rs:43-253) as a
+// host state machine over GPU line searches.
+//
+// The reference runs restarts on rayon threads and, inside a restart, calls evaluate_mean up
+// to 1 + 2*T times per feature, one weight vector at a time.  The candidate weights of a
+// feature depend only on (orig, step_base, step_scale, T), never on a score, so here every
+// restart submits its whole next group of candidates to the GPU at once
+// (fr_dev_eval_coord_sweeps: one pass over the feature matrix per restart and group), and the
+// reference's sequential accept / early-break logic is replayed on the returned means.
+//   group A = direction 0 (weight -> 0) + direction -1   (1 + T candidates)
+//   group B = direction +1                               (T candidates), only when the
+//             reference would get there (coordinate_ascent.rs:174-176).
+// Direction -1 of group A is speculative with respect to the break after direction 0; the
+// statistics keep "consumed" (what the reference's control flow evaluates) and "computed"
+// apart.
+#include <cmath>
+#include <cstdio>
+#include <mutex>
+
+#include "host.hpp"
+
+namespace frb {
+
+namespace {
+
+std::mutex g_stats_mu;
+TrainStats g_last_stats;
+
+void l1_normalize(std::vector<double> &w) {  // coordinate_ascent.rs:72-82
+    double sum = 0.0;
+    for (double x : w) sum += std::fabs(x);
+    if (sum > 0.0)
+        for (double &x : w) x /= sum;
+}
+
+struct Restart {
+    uint32_t id = 0;
+    Rand64 rng;
+    std::vector<double> best_w;
+    double best_score = 0.0;
+    std::vector<uint32_t> order;
+    size_t fi = 0;
+    size_t successes = 0;
+    bool done = false;
+    // line search in flight
+    std::vector<double> model;
+    double start_score = 0.0;
+    double orig = 0.0;
+    uint32_t feature = 0;
+    int group = 0;  // 0 = A pending, 1 = B pending
+    std::vector<double> cands;
+    explicit Restart(unsigned __int128 seed) : rng(seed) {}
+};
+
+// coordinate_ascent.rs:145-171: the weights one direction tries
+void direction_candidates(const CoordinateAscentParams &p, double orig, int dir, std::vector<double> &out) {
+    double step = p.step_base * (double)dir;
+    if (orig != 0.0 && std::fabs(step) > 0.5 * std::fabs(orig)) step = p.step_base * std::fabs(orig) * (double)dir;
+    double total = step;
+    uint32_t iters = p.num_max_iterations;
+    if (dir == 0) {
+        iters = 1;
+        total = -orig;
+    }
+    for (uint32_t it = 0; it < iters; ++it) {
+        out.push_back(orig + total);
+        step *= p.step_scale;
+        total += step;
+    }
+}
+
+bool replace_if_better(Restart &r, double score, double w) {  // core.rs:57-66
+    if (score == score && score > r.best_score) {
+        r.best_score = score;
+        r.best_w = r.model;
+        r.best_w[r.feature] = w;
+        return true;
+    }
+    return false;
+}
+
+}  // namespace
+
+TrainStats last_train_stats() {
+    std::lock_guard<std::mutex> lock(g_stats_mu);
+    return g_last_stats;
+}
+
+void set_last_train_stats(const TrainStats &s) {
+    std::lock_guard<std::mutex> lock(g_stats_mu);
+    g_last_stats = s;
+}
+
+Model coordinate_ascent_learn(const CoordinateAscentParams &p, const DatasetView &view,
+                              const Evaluator &ev, TrainStats *stats_out) {
+    TrainStats stats;
+    const std::vector<uint32_t> fids = view.feature_ids();
+    if (fids.empty()) throw Error("Should be at least one feature!");
+    if (view.num_instances() == 0) throw Error("dataset has no instances");
+    if (ev.num_queries() == 0 && ev.global_queries() == 0) throw Error("dataset has no queries");
+    if (p.num_restarts == 0) throw Error("Should be at least 1 restart!");
+    uint32_t dim = 0;
+    for (uint32_t f : fids) dim = std::max(dim, f + 1);  // coordinate_ascent.rs:97-103
+    const std::string measure_name = ev.measure().display;
+
+    if (!p.quiet) {
+        printf("---------------------------\nTraining starts...\n---------------------------\n");
+    }
+    Rand64 master((unsigned __int128)p.seed);
+    std::vector<Restart> rs;
+    rs.reserve(p.num_restarts);
+    for (uint32_t r = 0; r < p.num_restarts; ++r) {
+        rs.emplace_back((unsigned __int128)master.rand_u64());  // coordinate_ascent.rs:211-213
+        rs.back().id = r;
+        if (!p.quiet) printf("[+] Random restart #%u/%u...\n", r + 1, p.num_restarts);
+    }
+    // reset(): coordinate_ascent.rs:50-70, then the start score (:110) for every restart at once
+    std::vector<std::vector<double>> init(p.num_restarts, std::vector<double>(dim, 0.0));
+    for (uint32_t r = 0; r < p.num_restarts; ++r) {
+        for (uint32_t f : fids)
+            init[r][f] = p.init_random ? (rs[r].rng.rand_float() * 2.0) - 1.0 : 1.0 / (double)fids.size();
+    }
+    {
+        const std::vector<double> start = ev.evaluate_linear(init);
+        stats.evals_consumed += p.num_restarts;
+        stats.evals_computed += p.num_restarts;
+        for (uint32_t r = 0; r < p.num_restarts; ++r) {
+            rs[r].best_w = init[r];
+            rs[r].best_score = start[r];
+        }
+    }
+
+    const size_t T = p.num_max_iterations;
+    const size_t stride = 1 + T;
+    std::vector<double> base_w, cand_w;
+    std::vector<uint32_t> fid_arr, ncand;
+    std::vector<int64_t> sums;
+    std::vector<Restart *> active;
+    for (;;) {
+        active.clear();
+        for (Restart &r : rs)
+            if (!r.done) active.push_back(&r);
+        if (active.empty()) break;
+        // 1. every active restart prepares its next group of candidates
+        base_w.assign(active.size() * dim, 0.0);
+        cand_w.assign(active.size() * stride, 0.0);
+        fid_arr.assign(active.size(), 0);
+        ncand.assign(active.size(), 0);
+        for (size_t a = 0; a < active.size(); ++a) {
+            Restart &r = *active[a];
+            if (r.group == 0) {
+                if (r.fi == 0) {
+                    r.order = fids;
+                    shuffle(r.order, r.rng);  // coordinate_ascent.rs:114-116
+                    r.successes = 0;
+                    if (!p.quiet) {
+                        printf("Shuffle features and optimize!\n----------------------------------------\n");
+                        printf("%4u|%-16s|%9s|%9s\n", r.id, "Feature", "Weight", measure_name.c_str());
+                        printf("----------------------------------------\n");
+                    }
+                }
+                r.feature = r.order[r.fi];
+                r.start_score = r.best_score;
+                r.model = r.best_w;
+                if (p.normalize) l1_normalize(r.model);  // :134-138 (the clone, not the best)
+                r.orig = r.model[r.feature];
+                r.cands.clear();
+                direction_candidates(p, r.orig, 0, r.cands);
+                direction_candidates(p, r.orig, -1, r.cands);
+            } else {
+                r.cands.clear();
+                direction_candidates(p, r.orig, +1, r.cands);
+            }
+            std::copy(r.model.begin(), r.model.end(), base_w.begin() + a * dim);
+            std::copy(r.cands.begin(), r.cands.end(), cand_w.begin() + a * stride);
+            fid_arr[a] = r.feature;
+            ncand[a] = (uint32_t)r.cands.size();
+            stats.evals_computed += r.cands.size();
+        }
+        // 2. one GPU pass per restart
+        sums.assign(active.size() * stride, 0);
+        if (fr_dev_eval_coord_sweeps(ev.plan(), active.size(), base_w.data(), dim, fid_arr.data(),
+                                     cand_w.data(), ncand.data(), stride, sums.data()))
+            throw Error(fr_dev_last_error());
+        stats.sweeps += active.size();
+        stats.global_steps += 1;
+        // 3. replay the reference's sequential control flow on the means
+        for (size_t a = 0; a < active.size(); ++a) {
+            Restart &r = *active[a];
+            const std::string fname = p.quiet ? std::string() : view.parent->feature_name(r.feature);
+            auto take = [&](size_t k) {
+                const double score = ev.mean_from_fx(sums[a * stride + k]);
+                stats.evals_consumed += 1;
+                if (replace_if_better(r, score, r.cands[k]) && !p.quiet)
+                    printf("%4u|%-16s|%9.3f|%9.3f\n", r.id, fname.c_str(), r.cands[k], score);
+            };
+            bool feature_done = false;
+            if (r.group == 0) {
+                take(0);  // direction 0
+                if ((r.best_score - r.start_score) > p.tolerance) {
+                    feature_done = true;  // :174-176
+                } else {
+                    for (size_t k = 1; k < r.cands.size(); ++k) take(k);  // direction -1
+                    if ((r.best_score - r.start_score) > p.tolerance) feature_done = true;
+                    else if (T == 0) feature_done = true;
+                    else r.group = 1;
+                }
+            } else {
+                for (size_t k = 0; k < r.cands.size(); ++k) take(k);  // direction +1
+                feature_done = true;
+            }
+            if (feature_done) {
+                if ((r.best_score - r.start_score) > p.tolerance) r.successes += 1;  // :181-183
+                r.group = 0;
+                r.fi += 1;
+                if (r.fi == r.order.size()) {
+                    r.fi = 0;
+                    if (r.successes == 0) r.done = true;  // :185-187
+                    else if (!p.quiet) printf("---------------------------\n");
+                }
+            }
+        }
+    }
+    if (!p.quiet) printf("---------------------------\nFinished successfully.\n");
+
+    Model out;
+    if (p.output_ensemble && rs.size() > 1) {  // :232-242
+        out.kind = Model::Ensemble;
+        for (Restart &r : rs) {
+            std::vector<double> w = r.best_w;
+            l1_normalize(w);
+            out.members.push_back(Model::linear(std::move(w)));
+            out.weights.push_back(r.best_score);
+        }
+    } else {  // :244-251, Iterator::max keeps the LAST maximal element
+        size_t best = 0;
+        for (size_t r = 1; r < rs.size(); ++r)
+            if (rs[r].best_score >= rs[best].best_score) best = r;
+        out = Model::linear(rs[best].best_w);
+    }
+    if (stats_out) *stats_out = stats;
+    set_last_train_stats(stats);
+    return out;
+}
+
+}  // namespace frb

@@ -1,0 +1,1324 @@
+// device.cu -- the sm_100a kernels and the fr_dev_* kernel ABI (include/fastrank_b200.h).
+//
+// What runs here is the reference's hot path, restated for the GPU:
+//   score   dense_dataset.rs:67-76 + model.rs:47-51   (left-to-right f64 dot over f32 features,
+//                                                      separate multiply and add, no FMA)
+//           model.rs:64-84, :104-112                   (tree walk, weighted ensemble)
+//   rank    evaluators.rs:33-49, :206-221              (score desc, gain asc, instance id asc)
+//   metric  evaluators.rs:235-272, :342-381, :418-448  (RR, DCG/NDCG, AP)
+//   mean    evaluators.rs:173-184
+//
+// Data layout in HBM:
+//   X        float32, feature-major ("column-major"): X[j * ld + p], p = document position.
+//            Positions are grouped by query and, inside a query, ordered by (gain asc,
+//            instance id asc).  That is the reference's tie-break, so the reference's ranking is
+//            exactly a STABLE descending sort by score of a query's positions.
+//   gain     float32[p], gexp float64[p] = 2^gain - 1 (computed once on the host with libm).
+//   plan     a SetEvaluator: queries packed into tiles of <= TB documents; one CTA ranks one
+//            tile for KC candidate models at a time.
+//
+// Determinism: per-query metric values are bit-identical to the oracle; they are summed as
+// signed fixed point (2^-40) with integer atomics, so the mean does not depend on launch
+// geometry, atomics order or the number of GPUs.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fastrank_b200.h"
+#include "model_program.hpp"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_kernel_launches{0};
+
+int fail(const std::string &msg) {
+    g_last_error = msg;
+    return 1;
+}
+
+#define CU(expr)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return fail(std::string(#expr) + " failed: " + cudaGetErrorString(e__));      \
+    } while (0)
+
+#define LAUNCHED() g_kernel_launches.fetch_add(1, std::memory_order_relaxed)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        return cudaMalloc((void **)&p, sizeof(T) * (count ? count : 1));
+    }
+    cudaError_t upload(const std::vector<T> &h, cudaStream_t s = 0) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpyAsync(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, s);
+    }
+    cudaError_t ensure(size_t count) { return count <= n && p ? cudaSuccess : alloc(count); }
+};
+
+template <typename T>
+struct PinnedBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~PinnedBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    cudaError_t ensure(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = count;
+        return cudaMallocHost((void **)&p, sizeof(T) * (count ? count : 1));
+    }
+};
+
+constexpr int kMaxTile = 1024;
+constexpr double kFxScale = 1099511627776.0; /* 2^FR_FX_BITS */
+static_assert(FR_FX_BITS == 40, "kFxScale must match FR_FX_BITS");
+
+// ---------------------------------------------------------------------------------------
+// NCCL, bound at run time so the library loads on machines without it.
+// ---------------------------------------------------------------------------------------
+struct NcclApi {
+    typedef struct {
+        char internal[128];
+    } UniqueId;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+NcclApi &nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        void *h = nullptr;
+        for (const char *nm : names) {
+            h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) {
+            const char *env = getenv("FASTRANK_NCCL_LIB");
+            if (env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+        }
+        if (!h) {
+            api.why = "libnccl.so.2 not found (import torch first or set FASTRANK_NCCL_LIB)";
+            return;
+        }
+        api.GetUniqueId = (int (*)(NcclApi::UniqueId *))dlsym(h, "ncclGetUniqueId");
+        api.CommInitRank =
+            (int (*)(void **, int, NcclApi::UniqueId, int))dlsym(h, "ncclCommInitRank");
+        api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *,
+                                 cudaStream_t))dlsym(h, "ncclAllReduce");
+        api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+        api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
+        if (!api.ok) api.why = "libnccl is missing expected symbols";
+    });
+    return api;
+}
+constexpr int kNcclInt64 = 4;
+constexpr int kNcclUint64 = 5;
+constexpr int kNcclSum = 0;
+
+}  // namespace
+
+struct fr_dev_comm {
+    int device = 0;
+    int rank = 0;
+    int world = 1;
+    void *comm = nullptr;
+    cudaStream_t stream = nullptr;
+    DevBuf<uint64_t> scratch;
+};
+
+struct fr_dev_dataset {
+    int device = 0;
+    size_t n = 0, d = 0, ld = 0;
+    uint32_t nq = 0;
+    DevBuf<float> x;        // [d][ld]
+    DevBuf<float> gain;     // [n] by position
+    DevBuf<double> gexp;    // [n] by position
+    DevBuf<uint32_t> inst_of_pos_dev;
+    std::vector<uint32_t> inst_of_pos, pos_of_inst;
+    std::vector<uint32_t> q_start, q_len;  // per query, in positions
+    std::vector<float> gain_pos;           // host copy, by position
+    cudaStream_t stream = nullptr;
+    DevBuf<double> scores_pos;   // scratch for model scoring
+    DevBuf<double> scores_inst;  // scratch for predict
+    // device-side timing (fr_dev_timer_*, fr_dev_profile_*)
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    ~fr_dev_dataset() {
+        for (auto &pr : prof_events) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        if (t0) cudaEventDestroy(t0);
+        if (t1) cudaEventDestroy(t1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    // event pair bracketing one kernel launch while profiling is on
+    std::pair<cudaEvent_t, cudaEvent_t> *prof_slot() {
+        if (!profile) return nullptr;
+        if (prof_used == prof_events.size()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return nullptr;
+            prof_events.emplace_back(a, b);
+        }
+        return &prof_events[prof_used++];
+    }
+};
+
+struct fr_dev_model {
+    fr_dev_dataset *ds = nullptr;
+    DevBuf<uint64_t> code;
+    size_t n_words = 0;
+};
+
+// Device-side view of a plan (passed to kernels by value).
+struct PlanView {
+    const float *x;
+    size_t ld;
+    uint32_t dfeat;
+    const float *gain;
+    const double *gexp;
+    const double *lg2;           // log2(i + 2)
+    const uint32_t *tile_doc_off;  // nt + 1
+    const uint32_t *tile_q_off;    // nt + 1
+    const uint32_t *pd_pos;        // plan doc -> position
+    const uint32_t *pd_q;          // plan doc -> (local query start) | (local query end << 16)
+    const uint32_t *pq_local;      // plan query -> (local start) | (len << 16)
+    const uint32_t *pq_doc0;       // plan query -> first plan doc
+    const double *pq_norm;         // ideal DCG (NaN = none) or num_relevant
+    const uint32_t *pq_view;       // plan query -> view (output) index
+    uint32_t nt;
+    uint32_t nq_plan;
+    uint32_t nq_view;
+    int metric;
+    int depth;  // INT_MAX when absent
+};
+
+struct fr_dev_plan {
+    fr_dev_dataset *ds = nullptr;
+    int metric = 0;
+    int depth = INT_MAX;
+    int tb = 128;
+    uint32_t nq_view = 0, nq_plan = 0, nt = 0;
+    uint32_t max_len = 0;
+    DevBuf<double> lg2;
+    DevBuf<uint32_t> tile_doc_off, tile_q_off, pd_pos, pd_q, pq_local, pq_doc0, pq_view;
+    DevBuf<double> pq_norm;
+    // work buffers
+    DevBuf<double> w_dev, cand_dev, perq_dev;
+    DevBuf<uint32_t> fid_dev, ncand_dev;
+    DevBuf<long long> sums_dev;
+    DevBuf<int> err_dev;
+    PinnedBuf<long long> sums_host;
+    PinnedBuf<int> err_host;
+    fr_dev_comm *comm = nullptr;
+    uint64_t nq_global = 0;
+    int sm_count = 148;
+    PlanView view() const {
+        PlanView v;
+        v.x = ds->x.p;
+        v.ld = ds->ld;
+        v.dfeat = (uint32_t)ds->d;
+        v.gain = ds->gain.p;
+        v.gexp = ds->gexp.p;
+        v.lg2 = lg2.p;
+        v.tile_doc_off = tile_doc_off.p;
+        v.tile_q_off = tile_q_off.p;
+        v.pd_pos = pd_pos.p;
+        v.pd_q = pd_q.p;
+        v.pq_local = pq_local.p;
+        v.pq_doc0 = pq_doc0.p;
+        v.pq_norm = pq_norm.p;
+        v.pq_view = pq_view.p;
+        v.nt = nt;
+        v.nq_plan = nq_plan;
+        v.nq_view = nq_view;
+        v.metric = metric;
+        v.depth = depth;
+        return v;
+    }
+};
+
+// =========================================================================================
+// Kernels
+// =========================================================================================
+namespace {
+
+constexpr int ERR_NAN_SCORE = 1;
+constexpr int ERR_DCG_ABOVE_IDEAL = 2;
+
+// Rows of the host matrix -> feature-major, regrouped by query.
+__global__ void gather_transpose_kernel(const float *__restrict__ src,
+                                        const uint32_t *__restrict__ inst_of_pos,
+                                        float *__restrict__ dst, size_t n, size_t d, size_t ld) {
+    __shared__ float tile[32][33];
+    size_t p0 = (size_t)blockIdx.x * 32, j0 = (size_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        size_t p = p0 + r, j = j0 + threadIdx.x;
+        float v = 0.f;
+        if (p < n && j < d) v = src[(size_t)inst_of_pos[p] * d + j];
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        size_t j = j0 + r, p = p0 + threadIdx.x;
+        if (j < d && p < ld) dst[j * ld + p] = (p < n) ? tile[threadIdx.x][r] : 0.f;
+    }
+}
+
+// Order-preserving map f64 -> u64 (larger score => larger key).  NotNan ordering treats
+// -0.0 and +0.0 as equal (evaluators.rs:36), so zeros are canonicalised first.
+__device__ __forceinline__ unsigned long long score_key(double s, int *err_flag) {
+    if (s != s) atomicOr(err_flag, ERR_NAN_SCORE);  // reference: panic "Model.predict -> NaN"
+    long long b = __double_as_longlong(s);
+    if ((b << 1) == 0) b = 0;
+    unsigned long long u = (unsigned long long)b;
+    return b < 0 ? ~u : (u | 0x8000000000000000ull);
+}
+
+// Rank one tile for up to KC candidates and fold the per-query metric into s_sum.
+//
+// keys[k][t] holds the key of local document t under candidate k.  Because local order is the
+// reference's tie-break order, rank(t) = #{j : key_j > key_t} + #{j < t : key_j == key_t}
+// (evaluators.rs:33-49).  Each document then drops its metric payload into slot rank(t) of its
+// query, and one thread per (query, candidate) folds the slots in rank order -- the same
+// left-to-right f64 sums the reference performs (evaluators.rs:265-270, :434-446).
+template <int KC>
+__device__ __forceinline__ void rank_and_metric(const PlanView &P, uint32_t tile, int tb, int t,
+                                                bool active, uint32_t qs, uint32_t qe, uint32_t pos,
+                                                const unsigned long long (&mykey)[KC], int K,
+                                                unsigned long long *s_keys,
+                                                unsigned long long *s_sum, double *g_perq,
+                                                int *g_err) {
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < KC; ++k)
+            if (k < K) s_keys[k * tb + t] = mykey[k];
+    }
+    __syncthreads();
+    unsigned cnt[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) cnt[k] = 0;
+    if (active) {
+        for (uint32_t j = qs; j < qe; ++j) {
+            const bool before = j < (uint32_t)t;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if (k < K) {
+                    unsigned long long kj = s_keys[k * tb + j];
+                    cnt[k] += (kj > mykey[k]) | ((kj == mykey[k]) & before);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (active) {
+        const float g = __ldg(P.gain + pos);
+        if (P.metric == FR_METRIC_NDCG) {
+            const double ge = __ldg(P.gexp + pos);
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if (k < K) {
+                    double term = 0.0;
+                    // compute_dcg, evaluators.rs:265-270: (2^gain - 1) / log2(i + 2)
+                    if ((int)cnt[k] < P.depth && ge != 0.0) term = ge / __ldg(P.lg2 + cnt[k]);
+                    s_keys[k * tb + qs + cnt[k]] = (unsigned long long)__double_as_longlong(term);
+                }
+            }
+        } else {
+            const unsigned long long rel = g > 0.0f ? 1ull : 0ull;  // evaluators.rs:91-93
+#pragma unroll
+            for (int k = 0; k < KC; ++k)
+                if (k < K) s_keys[k * tb + qs + cnt[k]] = rel;
+        }
+    }
+    __syncthreads();
+    const uint32_t q0 = P.tile_q_off[tile];
+    const uint32_t nqt = P.tile_q_off[tile + 1] - q0;
+    for (uint32_t u = t; u < nqt * (uint32_t)K; u += tb) {
+        const uint32_t ql = u / (uint32_t)K, k = u - ql * (uint32_t)K;
+        const uint32_t pq = q0 + ql;
+        const uint32_t loc = P.pq_local[pq];
+        const uint32_t start = loc & 0xffffu, len = loc >> 16;
+        const unsigned long long *slots = s_keys + k * tb + start;
+        const double norm = P.pq_norm[pq];
+        double value = 0.0;
+        if (P.metric == FR_METRIC_NDCG) {
+            if (norm == norm) {  // Some(ideal)
+                const uint32_t lim = len < (uint32_t)P.depth ? len : (uint32_t)P.depth;
+                double dcg = 0.0;
+                for (uint32_t r = 0; r < lim; ++r)
+                    dcg = __dadd_rn(dcg, __longlong_as_double((long long)slots[r]));
+                if (dcg > norm) atomicOr(g_err, ERR_DCG_ABOVE_IDEAL);  // evaluators.rs:369-374
+                value = dcg / norm;
+            }
+        } else if (P.metric == FR_METRIC_AP) {
+            if (norm > 0.0) {
+                unsigned recall = 0;
+                double sum = 0.0;
+                for (uint32_t r = 0; r < len; ++r) {
+                    if (slots[r]) {
+                        recall += 1;
+                        sum = __dadd_rn(sum, (double)recall / (double)(r + 1));
+                    }
+                }
+                value = sum / norm;
+            }
+        } else {
+            for (uint32_t r = 0; r < len; ++r) {
+                if (slots[r]) {
+                    value = 1.0 / (double)(r + 1);
+                    break;
+                }
+            }
+        }
+        if (g_perq) g_perq[(size_t)k * P.nq_view + P.pq_view[pq]] = value;
+        const long long fx = __double2ll_rn(value * kFxScale);
+        atomicAdd(&s_sum[k], (unsigned long long)fx);
+    }
+    __syncthreads();
+}
+
+struct SweepArgs {
+    const double *base_w;   // [n_sweeps][wlen]
+    const uint32_t *fid;    // [n_sweeps]
+    const double *cand_w;   // [n_sweeps][cand_stride]
+    const uint32_t *n_cand; // [n_sweeps]
+    long long *sums;        // [n_sweeps][cand_stride]
+    uint32_t wlen;
+    uint32_t cand_stride;
+    uint32_t cand_off;      // this launch handles candidates [cand_off, cand_off + KC)
+    int *err;
+};
+
+// One coordinate-ascent line search per blockIdx.y (coordinate_ascent.rs:131-177).  All
+// candidates of a sweep differ from base_w only in coordinate f, so per document the prefix
+// sum over j < f and every product x_j * w_j are computed once; only the additions after f
+// are per candidate.  The additions happen in the reference's order, so every score is
+// bit-identical to dense_dataset.rs:67-76.
+template <int KC, int TB>
+__global__ void __launch_bounds__(TB) coord_sweep_kernel(PlanView P, SweepArgs A) {
+    extern __shared__ unsigned long long smem[];
+    unsigned long long *s_keys = smem;             // KC * TB
+    unsigned long long *s_sum = smem + KC * TB;    // KC
+    const int t = threadIdx.x;
+    const uint32_t sweep = blockIdx.y;
+    const int ncand = (int)A.n_cand[sweep] - (int)A.cand_off;
+    if (ncand <= 0) return;
+    const int K = ncand < KC ? ncand : KC;
+    const double *__restrict__ w = A.base_w + (size_t)sweep * A.wlen;
+    const double *__restrict__ cw = A.cand_w + (size_t)sweep * A.cand_stride + A.cand_off;
+    const uint32_t dm = A.wlen < P.dfeat ? A.wlen : P.dfeat;  // zip() truncation
+    const uint32_t f = A.fid[sweep];
+    if (t < KC) s_sum[t] = 0ull;
+    __syncthreads();
+    for (uint32_t tile = blockIdx.x; tile < P.nt; tile += gridDim.x) {
+        const uint32_t doc0 = P.tile_doc_off[tile];
+        const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
+        const bool active = t < nd;
+        uint32_t pos = 0, qs = 0, qe = 0;
+        unsigned long long key[KC];
+        if (active) {
+            pos = P.pd_pos[doc0 + t];
+            const uint32_t qp = P.pd_q[doc0 + t];
+            qs = qp & 0xffffu;
+            qe = qp >> 16;
+            const float *__restrict__ xp = P.x + pos;
+            double acc = 0.0;
+            const uint32_t fsplit = f < dm ? f : dm;
+#pragma unroll 8
+            for (uint32_t j = 0; j < fsplit; ++j)
+                acc = __dadd_rn(acc, __dmul_rn((double)__ldg(xp + (size_t)j * P.ld), __ldg(w + j)));
+            double tk[KC];
+            if (f < dm) {
+                const double xf = (double)__ldg(xp + (size_t)f * P.ld);
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const double wk = k < K ? __ldg(cw + k) : 0.0;
+                    tk[k] = __dadd_rn(acc, __dmul_rn(xf, wk));
+                }
+#pragma unroll 4
+                for (uint32_t j = f + 1; j < dm; ++j) {
+                    const double p = __dmul_rn((double)__ldg(xp + (size_t)j * P.ld), __ldg(w + j));
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) tk[k] = __dadd_rn(tk[k], p);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < KC; ++k) tk[k] = acc;
+            }
+#pragma unroll
+            for (int k = 0; k < KC; ++k) key[k] = k < K ? score_key(tk[k], A.err) : 0ull;
+        } else {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) key[k] = 0ull;
+        }
+        rank_and_metric<KC>(P, tile, TB, t, active, qs, qe, pos, key, K, s_keys, s_sum, nullptr,
+                            A.err);
+    }
+    if (t < K)
+        atomicAdd((unsigned long long *)(A.sums + (size_t)sweep * A.cand_stride + A.cand_off + t),
+                  s_sum[t]);
+}
+
+struct BatchArgs {
+    const double *wt;   // [dm][KC] transposed candidate weights (zero padded)
+    long long *sums;    // [KC]
+    double *perq;       // nullptr or [KC][nq_view]
+    uint32_t dm;
+    int K;
+    int *err;
+};
+
+// evaluate_mean for KC arbitrary weight vectors in one pass over X (evaluators.rs:173-224).
+template <int KC, int TB>
+__global__ void __launch_bounds__(TB) linear_batch_kernel(PlanView P, BatchArgs A) {
+    extern __shared__ unsigned long long smem[];
+    unsigned long long *s_keys = smem;
+    unsigned long long *s_sum = smem + KC * TB;
+    const int t = threadIdx.x;
+    const int K = A.K;
+    if (t < KC) s_sum[t] = 0ull;
+    __syncthreads();
+    for (uint32_t tile = blockIdx.x; tile < P.nt; tile += gridDim.x) {
+        const uint32_t doc0 = P.tile_doc_off[tile];
+        const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
+        const bool active = t < nd;
+        uint32_t pos = 0, qs = 0, qe = 0;
+        unsigned long long key[KC];
+        if (active) {
+            pos = P.pd_pos[doc0 + t];
+            const uint32_t qp = P.pd_q[doc0 + t];
+            qs = qp & 0xffffu;
+            qe = qp >> 16;
+            const float *__restrict__ xp = P.x + pos;
+            double tk[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) tk[k] = 0.0;
+#pragma unroll 4
+            for (uint32_t j = 0; j < A.dm; ++j) {
+                const double xv = (double)__ldg(xp + (size_t)j * P.ld);
+                const double *__restrict__ wj = A.wt + (size_t)j * KC;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) tk[k] = __dadd_rn(tk[k], __dmul_rn(xv, __ldg(wj + k)));
+            }
+#pragma unroll
+            for (int k = 0; k < KC; ++k) key[k] = k < K ? score_key(tk[k], A.err) : 0ull;
+        } else {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) key[k] = 0ull;
+        }
+        rank_and_metric<KC>(P, tile, TB, t, active, qs, qe, pos, key, K, s_keys, s_sum, A.perq,
+                            A.err);
+    }
+    if (t < K) atomicAdd((unsigned long long *)(A.sums + t), s_sum[t]);
+}
+
+// Rank + metric for scores that already sit in HBM (scores[position]); used after the model
+// interpreter (trees, ensembles, single-feature models).
+template <int TB>
+__global__ void __launch_bounds__(TB) scores_eval_kernel(PlanView P, const double *__restrict__ scores,
+                                                         long long *sums, double *perq, int *err) {
+    extern __shared__ unsigned long long smem[];
+    unsigned long long *s_keys = smem;
+    unsigned long long *s_sum = smem + TB;
+    const int t = threadIdx.x;
+    if (t == 0) s_sum[0] = 0ull;
+    __syncthreads();
+    for (uint32_t tile = blockIdx.x; tile < P.nt; tile += gridDim.x) {
+        const uint32_t doc0 = P.tile_doc_off[tile];
+        const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
+        const bool active = t < nd;
+        uint32_t pos = 0, qs = 0, qe = 0;
+        unsigned long long key[1] = {0ull};
+        if (active) {
+            pos = P.pd_pos[doc0 + t];
+            const uint32_t qp = P.pd_q[doc0 + t];
+            qs = qp & 0xffffu;
+            qe = qp >> 16;
+            key[0] = score_key(__ldg(scores + pos), err);
+        }
+        rank_and_metric<1>(P, tile, TB, t, active, qs, qe, pos, key, 1, s_keys, s_sum, perq, err);
+    }
+    if (t == 0) atomicAdd((unsigned long long *)sums, s_sum[0]);
+}
+
+// ModelEnum interpreter: one thread per document position (model.rs:18-112).
+__global__ void model_score_kernel(const float *__restrict__ x, size_t ld, uint32_t dfeat, size_t n,
+                                   const uint64_t *__restrict__ code,
+                                   const uint32_t *__restrict__ inst_of_pos,
+                                   double *__restrict__ out_pos, double *__restrict__ out_inst) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float *__restrict__ xp = x + p;
+    double st[frb::FR_MODEL_STACK];
+    int sp = 0;
+    size_t pc = 0;
+    for (;;) {
+        const uint64_t word = __ldg(code + pc);
+        const uint32_t op = (uint32_t)(word & 0xff);
+        const uint64_t arg = word >> 8;
+        if (op == frb::OP_END) break;
+        if (op == frb::OP_LINEAR) {
+            const uint32_t nw = (uint32_t)arg;
+            const uint32_t m = nw < dfeat ? nw : dfeat;
+            double acc = 0.0;
+#pragma unroll 4
+            for (uint32_t j = 0; j < m; ++j) {
+                const double wv = __longlong_as_double((long long)__ldg(code + pc + 1 + j));
+                acc = __dadd_rn(acc, __dmul_rn((double)__ldg(xp + (size_t)j * ld), wv));
+            }
+            st[sp++] = acc;
+            pc += 1 + nw;
+        } else if (op == frb::OP_SINGLE) {
+            const uint32_t fid = (uint32_t)arg;
+            const double dir = __longlong_as_double((long long)__ldg(code + pc + 1));
+            const double v = fid < dfeat ? (double)__ldg(xp + (size_t)fid * ld) : 0.0;
+            st[sp++] = __dmul_rn(dir, v);
+            pc += 2;
+        } else if (op == frb::OP_TREE) {
+            const uint64_t *nodes = code + pc + 1;
+            uint32_t node = 0;
+            double leaf;
+            for (;;) {
+                const uint64_t w0 = __ldg(nodes + 2 * (size_t)node);
+                const uint64_t w1 = __ldg(nodes + 2 * (size_t)node + 1);
+                const uint32_t fid = (uint32_t)w0;
+                if (fid == frb::FR_LEAF) {
+                    leaf = __longlong_as_double((long long)w1);
+                    break;
+                }
+                const float split = __uint_as_float((uint32_t)(w0 >> 32));
+                const float v = fid < dfeat ? __ldg(xp + (size_t)fid * ld) : 0.0f;
+                node = (v <= split) ? (uint32_t)w1 : (uint32_t)(w1 >> 32);
+            }
+            st[sp++] = leaf;
+            pc += 1 + 2 * (size_t)arg;
+        } else if (op == frb::OP_ENS_BEGIN) {
+            st[sp++] = 0.0;
+            pc += 1;
+        } else {  // OP_ENS_ACC
+            const double wv = __longlong_as_double((long long)__ldg(code + pc + 1));
+            const double v = st[--sp];
+            st[sp - 1] = __dadd_rn(st[sp - 1], __dmul_rn(wv, v));
+            pc += 2;
+        }
+    }
+    const double s = st[0];
+    if (out_pos) out_pos[p] = s;
+    if (out_inst) out_inst[inst_of_pos[p]] = s;
+}
+
+// Per-query norms from the dataset's own gains (NDCG::new evaluators.rs:319-338,
+// AveragePrecision::new :402-410), with optional overrides that came from a qrel.
+__global__ void plan_norms_kernel(PlanView P, const uint8_t *__restrict__ ov_present,
+                                  const double *__restrict__ ov_value, double *__restrict__ out) {
+    const uint32_t pq = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pq >= P.nq_plan) return;
+    const uint32_t len = P.pq_local[pq] >> 16;
+    const uint32_t doc0 = P.pq_doc0[pq];
+    const uint32_t view = P.pq_view[pq];
+    const bool has_ov = ov_present != nullptr && ov_present[view] != 0;
+    double norm;
+    if (P.metric == FR_METRIC_NDCG) {
+        if (has_ov) {
+            norm = ov_value[view];
+        } else {
+            // positions are gain-ascending, so the ideal ordering is the reverse walk
+            const bool any_pos = len > 0 && P.gain[P.pd_pos[doc0 + len - 1]] > 0.0f;
+            if (!any_pos) {
+                norm = __longlong_as_double(0x7ff8000000000000ll);
+            } else {
+                const uint32_t lim = len < (uint32_t)P.depth ? len : (uint32_t)P.depth;
+                double dcg = 0.0;
+                for (uint32_t i = 0; i < lim; ++i)
+                    dcg = __dadd_rn(dcg, P.gexp[P.pd_pos[doc0 + len - 1 - i]] / P.lg2[i]);
+                norm = dcg;
+            }
+        }
+    } else if (P.metric == FR_METRIC_AP) {
+        uint32_t rel = 0;
+        for (uint32_t i = 0; i < len; ++i) rel += P.gain[P.pd_pos[doc0 + i]] > 0.0f;
+        norm = (has_ov && ov_value[view] > 0.0) ? ov_value[view] : (double)rel;
+    } else {
+        norm = 0.0;
+    }
+    out[pq] = norm;
+}
+
+size_t eval_smem_bytes(int kc, int tb) { return sizeof(unsigned long long) * ((size_t)kc * tb + kc); }
+
+template <typename KernelT>
+int grid_for(KernelT kernel, int tb, size_t smem, int sm_count, uint32_t nt, uint32_t split,
+             uint32_t *out_gx) {
+    if (smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, tb, smem));
+    if (occ < 1) return fail("kernel does not fit on an SM");
+    // persistent CTAs: a whole number of waves over the SMs, shared between `split` sweeps
+    uint64_t total = (uint64_t)sm_count * (uint64_t)occ;
+    uint32_t gx = (uint32_t)std::max<uint64_t>(1, (total + split - 1) / split);
+    if (gx > nt) gx = nt;
+    if (gx < 1) gx = 1;
+    *out_gx = gx;
+    return 0;
+}
+
+const int kKcOptions[] = {2, 4, 8, 16, 26};
+
+int max_kc_for_tb(int tb) {
+    if (tb <= 256) return 26;
+    if (tb == 512) return 8;
+    return 4;
+}
+
+int pick_kc(int want, int tb) {
+    const int cap = max_kc_for_tb(tb);
+    for (int kc : kKcOptions)
+        if (kc >= want && kc <= cap) return kc;
+    return cap;
+}
+
+#define DISPATCH_KC_TB(KC_, TB_, ...)                           \
+    if (kc == KC_ && tb == TB_) {                               \
+        constexpr int KC = KC_;                                 \
+        constexpr int TB = TB_;                                 \
+        __VA_ARGS__;                                            \
+    } else
+
+#define DISPATCH_ALL(...)                                                                   \
+    DISPATCH_KC_TB(2, 128, __VA_ARGS__) DISPATCH_KC_TB(4, 128, __VA_ARGS__)                 \
+    DISPATCH_KC_TB(8, 128, __VA_ARGS__) DISPATCH_KC_TB(16, 128, __VA_ARGS__)                \
+    DISPATCH_KC_TB(26, 128, __VA_ARGS__) DISPATCH_KC_TB(2, 256, __VA_ARGS__)                \
+    DISPATCH_KC_TB(4, 256, __VA_ARGS__) DISPATCH_KC_TB(8, 256, __VA_ARGS__)                 \
+    DISPATCH_KC_TB(16, 256, __VA_ARGS__) DISPATCH_KC_TB(26, 256, __VA_ARGS__)               \
+    DISPATCH_KC_TB(2, 512, __VA_ARGS__) DISPATCH_KC_TB(4, 512, __VA_ARGS__)                 \
+    DISPATCH_KC_TB(8, 512, __VA_ARGS__) DISPATCH_KC_TB(2, 1024, __VA_ARGS__)                \
+    DISPATCH_KC_TB(4, 1024, __VA_ARGS__) { return fail("unsupported (KC, TB) combination"); }
+
+int launch_sweep(fr_dev_plan *pl, int kc, int tb, uint32_t n_sweeps, const SweepArgs &args,
+                 cudaStream_t stream) {
+    const size_t smem = eval_smem_bytes(kc, tb);
+    PlanView pv = pl->view();
+    DISPATCH_ALL({
+        uint32_t gx = 1;
+        if (grid_for(coord_sweep_kernel<KC, TB>, TB, smem, pl->sm_count, pl->nt, n_sweeps, &gx))
+            return 1;
+        auto *ev = pl->ds->prof_slot();
+        if (ev) cudaEventRecord(ev->first, stream);
+        coord_sweep_kernel<KC, TB><<<dim3(gx, n_sweeps), TB, smem, stream>>>(pv, args);
+        if (ev) cudaEventRecord(ev->second, stream);
+        LAUNCHED();
+    })
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_batch(fr_dev_plan *pl, int kc, int tb, const BatchArgs &args, cudaStream_t stream) {
+    const size_t smem = eval_smem_bytes(kc, tb);
+    PlanView pv = pl->view();
+    DISPATCH_ALL({
+        uint32_t gx = 1;
+        if (grid_for(linear_batch_kernel<KC, TB>, TB, smem, pl->sm_count, pl->nt, 1, &gx)) return 1;
+        auto *ev = pl->ds->prof_slot();
+        if (ev) cudaEventRecord(ev->first, stream);
+        linear_batch_kernel<KC, TB><<<gx, TB, smem, stream>>>(pv, args);
+        if (ev) cudaEventRecord(ev->second, stream);
+        LAUNCHED();
+    })
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_scores_eval(fr_dev_plan *pl, const double *scores, long long *sums, double *perq,
+                       int *err, cudaStream_t stream) {
+    const int tb = pl->tb;
+    const size_t smem = eval_smem_bytes(1, tb);
+    PlanView pv = pl->view();
+    uint32_t gx = 1;
+#define SCORES_CASE(TB_)                                                                       \
+    if (tb == TB_) {                                                                           \
+        if (grid_for(scores_eval_kernel<TB_>, TB_, smem, pl->sm_count, pl->nt, 1, &gx)) return 1; \
+        auto *ev = pl->ds->prof_slot();                                                        \
+        if (ev) cudaEventRecord(ev->first, stream);                                            \
+        scores_eval_kernel<TB_><<<gx, TB_, smem, stream>>>(pv, scores, sums, perq, err);       \
+        if (ev) cudaEventRecord(ev->second, stream);                                           \
+        LAUNCHED();                                                                            \
+    } else
+    SCORES_CASE(128) SCORES_CASE(256) SCORES_CASE(512) SCORES_CASE(1024) {
+        return fail("unsupported tile size");
+    }
+#undef SCORES_CASE
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int check_err_flags(int flags) {
+    if (flags & ERR_NAN_SCORE) return fail("Model.predict -> NaN (a score was NaN)");
+    if (flags & ERR_DCG_ABOVE_IDEAL)
+        return fail("actual DCG exceeds ideal DCG for some query (inconsistent judgments)");
+    return 0;
+}
+
+// all-reduce the fixed-point sums on the plan's stream
+int allreduce_sums(fr_dev_plan *pl, long long *dev, size_t count, cudaStream_t stream) {
+    if (!pl->comm || pl->comm->world <= 1) return 0;
+    NcclApi &api = nccl();
+    if (!api.ok) return fail(api.why);
+    int rc = api.AllReduce(dev, dev, count, kNcclInt64, kNcclSum, pl->comm->comm, stream);
+    if (rc != 0)
+        return fail(std::string("ncclAllReduce: ") + (api.GetErrorString ? api.GetErrorString(rc) : "?"));
+    return 0;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char *fr_dev_last_error(void) { return g_last_error.c_str(); }
+
+uint64_t fr_dev_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int fr_dev_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const float *gains,
+                          const uint32_t *query_index, uint32_t n_queries, fr_dev_dataset **out) {
+    if (!out) return fail("fr_dev_dataset_create: out is NULL");
+    *out = nullptr;
+    if (!x || !gains || !query_index) return fail("fr_dev_dataset_create: NULL input");
+    if (n == 0 || d == 0) return fail("fr_dev_dataset_create: empty dataset");
+    if (n > 0xFFFFFFF0ull) return fail("fr_dev_dataset_create: too many instances");
+    if (fr_dev_device_count() <= 0)
+        return fail("no CUDA device available: fastrank_b200 has no CPU fallback");
+    CU(cudaSetDevice(device));
+    std::unique_ptr<fr_dev_dataset> ds(new fr_dev_dataset());
+    ds->device = device;
+    ds->n = n;
+    ds->d = d;
+    ds->ld = (n + 127) / 128 * 128;
+    ds->nq = n_queries;
+    CU(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
+    // group by query (counting sort keeps instance ids ascending), then stable-sort each query
+    // by gain: the reference's tie-break order (evaluators.rs:40-48)
+    ds->q_len.assign(n_queries, 0);
+    for (size_t i = 0; i < n; ++i) {
+        if (query_index[i] >= n_queries) return fail("fr_dev_dataset_create: query index out of range");
+        if (gains[i] != gains[i]) return fail("NaN in ys[" + std::to_string(i) + "]");
+        ds->q_len[query_index[i]]++;
+    }
+    ds->q_start.assign(n_queries, 0);
+    {
+        uint32_t run = 0;
+        for (uint32_t q = 0; q < n_queries; ++q) {
+            ds->q_start[q] = run;
+            run += ds->q_len[q];
+        }
+    }
+    ds->inst_of_pos.resize(n);
+    {
+        std::vector<uint32_t> fill(ds->q_start);
+        for (size_t i = 0; i < n; ++i) ds->inst_of_pos[fill[query_index[i]]++] = (uint32_t)i;
+    }
+    for (uint32_t q = 0; q < n_queries; ++q) {
+        auto b = ds->inst_of_pos.begin() + ds->q_start[q];
+        std::stable_sort(b, b + ds->q_len[q],
+                         [&](uint32_t a, uint32_t c) { return gains[a] < gains[c]; });
+    }
+    ds->pos_of_inst.resize(n);
+    ds->gain_pos.resize(n);
+    std::vector<double> gexp(n);
+    {
+        std::map<uint32_t, double> cache;  // 2^gain - 1 with the host libm, as the oracle does
+        for (size_t p = 0; p < n; ++p) {
+            const uint32_t inst = ds->inst_of_pos[p];
+            ds->pos_of_inst[inst] = (uint32_t)p;
+            const float g = gains[inst];
+            ds->gain_pos[p] = g;
+            uint32_t bits;
+            memcpy(&bits, &g, 4);
+            auto it = cache.find(bits);
+            if (it == cache.end()) it = cache.emplace(bits, std::pow(2.0, (double)g) - 1.0).first;
+            gexp[p] = it->second;
+        }
+    }
+    cudaStream_t s = ds->stream;
+    CU(ds->gain.upload(ds->gain_pos, s));
+    CU(ds->gexp.upload(gexp, s));
+    CU(ds->inst_of_pos_dev.upload(ds->inst_of_pos, s));
+    CU(ds->x.alloc(ds->ld * d));
+    {
+        DevBuf<float> staging;
+        CU(staging.alloc(n * d));
+        CU(cudaMemcpyAsync(staging.p, x, sizeof(float) * n * d, cudaMemcpyHostToDevice, s));
+        dim3 grid((unsigned)((ds->ld + 31) / 32), (unsigned)((d + 31) / 32));
+        gather_transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(staging.p, ds->inst_of_pos_dev.p,
+                                                            ds->x.p, n, d, ds->ld);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
+    }
+    *out = ds.release();
+    return 0;
+}
+
+void fr_dev_dataset_destroy(fr_dev_dataset *ds) {
+    if (!ds) return;
+    cudaSetDevice(ds->device);
+    delete ds;
+}
+
+size_t fr_dev_dataset_bytes(const fr_dev_dataset *ds) {
+    if (!ds) return 0;
+    return ds->ld * ds->d * 4 + ds->n * (4 + 8 + 4);
+}
+
+int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_plan **out) {
+    if (!out) return fail("fr_dev_plan_create: out is NULL");
+    *out = nullptr;
+    if (!ds || !desc) return fail("fr_dev_plan_create: NULL argument");
+    if (desc->metric < 0 || desc->metric > 2) return fail("fr_dev_plan_create: bad metric");
+    if (desc->depth == 0) return fail("fr_dev_plan_create: depth 0 is not a usable cut-off");
+    CU(cudaSetDevice(ds->device));
+    std::unique_ptr<fr_dev_plan> pl(new fr_dev_plan());
+    pl->ds = ds;
+    pl->metric = desc->metric;
+    pl->depth = desc->depth < 0 || desc->depth > INT_MAX ? INT_MAX : (int)desc->depth;
+    pl->nq_view = desc->n_queries;
+    {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, ds->device));
+        pl->sm_count = prop.multiProcessorCount;
+    }
+    // 1. collect the positions of every view query
+    std::vector<std::vector<uint32_t>> qpos(desc->n_queries);
+    uint32_t max_len = 0;
+    for (uint32_t v = 0; v < desc->n_queries; ++v) {
+        const uint32_t q = desc->query_ids ? desc->query_ids[v] : v;
+        if (q >= ds->nq) return fail("fr_dev_plan_create: query id out of range");
+        std::vector<uint32_t> &pos = qpos[v];
+        if (desc->inst_off) {
+            for (uint64_t k = desc->inst_off[v]; k < desc->inst_off[v + 1]; ++k) {
+                const uint32_t inst = desc->inst_ids[k];
+                if (inst >= ds->n) return fail("fr_dev_plan_create: instance id out of range");
+                const uint32_t p = ds->pos_of_inst[inst];
+                if (p < ds->q_start[q] || p >= ds->q_start[q] + ds->q_len[q])
+                    return fail("fr_dev_plan_create: instance does not belong to its query");
+                pos.push_back(p);
+            }
+            std::sort(pos.begin(), pos.end());
+            pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
+        } else {
+            pos.resize(ds->q_len[q]);
+            for (uint32_t k = 0; k < ds->q_len[q]; ++k) pos[k] = ds->q_start[q] + k;
+        }
+        max_len = std::max<uint32_t>(max_len, (uint32_t)pos.size());
+    }
+    if (max_len > (uint32_t)kMaxTile)
+        return fail("a query has " + std::to_string(max_len) + " documents; this build ranks at most " +
+                    std::to_string(kMaxTile) + " per query");
+    pl->max_len = max_len;
+    int tb = 128;
+    while (tb < (int)max_len) tb *= 2;
+    pl->tb = tb;
+    // 2. pack whole queries into tiles of <= tb documents, in view order
+    std::vector<uint32_t> tile_doc_off{0}, tile_q_off{0}, pd_pos, pd_q, pq_local, pq_doc0, pq_view;
+    uint32_t cur_docs = 0;
+    auto close_tile = [&]() {
+        tile_doc_off.push_back((uint32_t)pd_pos.size());
+        tile_q_off.push_back((uint32_t)pq_local.size());
+        cur_docs = 0;
+    };
+    for (uint32_t v = 0; v < desc->n_queries; ++v) {
+        const uint32_t len = (uint32_t)qpos[v].size();
+        if (cur_docs + len > (uint32_t)tb && cur_docs > 0) close_tile();
+        const uint32_t start = cur_docs;
+        pq_local.push_back(start | (len << 16));
+        pq_doc0.push_back((uint32_t)pd_pos.size());
+        pq_view.push_back(v);
+        for (uint32_t k = 0; k < len; ++k) {
+            pd_pos.push_back(qpos[v][k]);
+            pd_q.push_back(start | ((start + len) << 16));
+        }
+        cur_docs += len;
+    }
+    if (tile_q_off.back() != pq_local.size() || tile_doc_off.back() != pd_pos.size()) close_tile();
+    pl->nt = (uint32_t)tile_doc_off.size() - 1;
+    pl->nq_plan = (uint32_t)pq_local.size();
+    // 3. discount table with the host libm (evaluators.rs:269: log2(i + 2))
+    std::vector<double> lg2(std::max<uint32_t>(max_len, 1));
+    for (size_t i = 0; i < lg2.size(); ++i) lg2[i] = std::log2((double)i + 2.0);
+    cudaStream_t s = ds->stream;
+    CU(pl->lg2.upload(lg2, s));
+    CU(pl->tile_doc_off.upload(tile_doc_off, s));
+    CU(pl->tile_q_off.upload(tile_q_off, s));
+    CU(pl->pd_pos.upload(pd_pos, s));
+    CU(pl->pd_q.upload(pd_q, s));
+    CU(pl->pq_local.upload(pq_local, s));
+    CU(pl->pq_doc0.upload(pq_doc0, s));
+    CU(pl->pq_view.upload(pq_view, s));
+    CU(pl->pq_norm.alloc(pl->nq_plan));
+    CU(pl->err_dev.alloc(1));
+    CU(pl->err_host.ensure(1));
+    // 4. norms
+    DevBuf<uint8_t> ovp;
+    DevBuf<double> ovv;
+    if (desc->norm_present && desc->norm_value) {
+        std::vector<uint8_t> hp(desc->norm_present, desc->norm_present + desc->n_queries);
+        std::vector<double> hv(desc->norm_value, desc->norm_value + desc->n_queries);
+        CU(ovp.upload(hp, s));
+        CU(ovv.upload(hv, s));
+    }
+    if (pl->nq_plan > 0) {
+        plan_norms_kernel<<<(pl->nq_plan + 127) / 128, 128, 0, s>>>(pl->view(), ovp.p, ovv.p,
+                                                                   pl->pq_norm.p);
+        LAUNCHED();
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(s));
+    pl->nq_global = pl->nq_view;
+    *out = pl.release();
+    return 0;
+}
+
+void fr_dev_plan_destroy(fr_dev_plan *plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->ds->device);
+    delete plan;
+}
+
+uint64_t fr_dev_plan_global_queries(const fr_dev_plan *plan) { return plan ? plan->nq_global : 0; }
+
+int fr_dev_plan_set_comm(fr_dev_plan *plan, fr_dev_comm *comm) {
+    if (!plan) return fail("fr_dev_plan_set_comm: NULL plan");
+    plan->comm = comm;
+    plan->nq_global = plan->nq_view;
+    if (comm && comm->world > 1) {
+        uint64_t v = plan->nq_view;
+        if (fr_dev_comm_allreduce_u64(comm, &v, 1)) return 1;
+        plan->nq_global = v;
+    }
+    return 0;
+}
+
+int fr_dev_eval_linear_batch(fr_dev_plan *pl, const double *w, size_t wlen, size_t n_cand,
+                             int64_t *out_sum_fx, double *out_per_query) {
+    if (!pl || !w || !out_sum_fx) return fail("fr_dev_eval_linear_batch: NULL argument");
+    fr_dev_dataset *ds = pl->ds;
+    CU(cudaSetDevice(ds->device));
+    cudaStream_t s = ds->stream;
+    const uint32_t dm = (uint32_t)std::min<size_t>(wlen, ds->d);
+    const int cap = pick_kc(26, pl->tb);
+    CU(pl->sums_dev.ensure(n_cand));
+    CU(pl->sums_host.ensure(n_cand));
+    CU(cudaMemsetAsync(pl->sums_dev.p, 0, sizeof(long long) * n_cand, s));
+    CU(cudaMemsetAsync(pl->err_dev.p, 0, sizeof(int), s));
+    if (out_per_query) CU(pl->perq_dev.ensure(n_cand * (size_t)pl->nq_view));
+    std::vector<double> wt;
+    for (size_t c0 = 0; c0 < n_cand; c0 += cap) {
+        const int K = (int)std::min<size_t>(cap, n_cand - c0);
+        const int kc = pick_kc(K, pl->tb);
+        wt.assign((size_t)std::max<uint32_t>(dm, 1) * kc, 0.0);
+        for (uint32_t j = 0; j < dm; ++j)
+            for (int k = 0; k < K; ++k) wt[(size_t)j * kc + k] = w[(c0 + k) * wlen + j];
+        CU(pl->w_dev.ensure(wt.size()));
+        // the previous chunk's kernel may still read w_dev: order the copy behind it
+        CU(cudaMemcpyAsync(pl->w_dev.p, wt.data(), sizeof(double) * wt.size(),
+                           cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+        BatchArgs a;
+        a.wt = pl->w_dev.p;
+        a.sums = pl->sums_dev.p + c0;
+        a.perq = out_per_query ? pl->perq_dev.p + c0 * (size_t)pl->nq_view : nullptr;
+        a.dm = dm;
+        a.K = K;
+        a.err = pl->err_dev.p;
+        if (pl->nt > 0 && launch_batch(pl, kc, pl->tb, a, s)) return 1;
+    }
+    if (allreduce_sums(pl, pl->sums_dev.p, n_cand, s)) return 1;
+    CU(cudaMemcpyAsync(pl->sums_host.p, pl->sums_dev.p, sizeof(long long) * n_cand,
+                       cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(pl->err_host.p, pl->err_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (out_per_query)
+        CU(cudaMemcpyAsync(out_per_query, pl->perq_dev.p,
+                           sizeof(double) * n_cand * (size_t)pl->nq_view, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (check_err_flags(pl->err_host.p[0])) return 1;
+    for (size_t c = 0; c < n_cand; ++c) out_sum_fx[c] = pl->sums_host.p[c];
+    return 0;
+}
+
+int fr_dev_eval_coord_sweeps(fr_dev_plan *pl, size_t n_sweeps, const double *base_w, size_t wlen,
+                             const uint32_t *fid, const double *cand_w, const uint32_t *n_cand,
+                             size_t cand_stride, int64_t *out_sum_fx) {
+    if (!pl || !base_w || !fid || !cand_w || !n_cand || !out_sum_fx)
+        return fail("fr_dev_eval_coord_sweeps: NULL argument");
+    if (n_sweeps == 0) return 0;
+    fr_dev_dataset *ds = pl->ds;
+    CU(cudaSetDevice(ds->device));
+    cudaStream_t s = ds->stream;
+    uint32_t kmax = 0;
+    for (size_t r = 0; r < n_sweeps; ++r) {
+        if (n_cand[r] > cand_stride) return fail("fr_dev_eval_coord_sweeps: n_cand > cand_stride");
+        kmax = std::max(kmax, n_cand[r]);
+    }
+    const size_t total = n_sweeps * cand_stride;
+    CU(pl->w_dev.ensure(n_sweeps * wlen));
+    CU(pl->cand_dev.ensure(total));
+    CU(pl->fid_dev.ensure(n_sweeps));
+    CU(pl->ncand_dev.ensure(n_sweeps));
+    CU(pl->sums_dev.ensure(total));
+    CU(pl->sums_host.ensure(total));
+    CU(cudaMemcpyAsync(pl->w_dev.p, base_w, sizeof(double) * n_sweeps * wlen, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pl->cand_dev.p, cand_w, sizeof(double) * total, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pl->fid_dev.p, fid, sizeof(uint32_t) * n_sweeps, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pl->ncand_dev.p, n_cand, sizeof(uint32_t) * n_sweeps, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(pl->sums_dev.p, 0, sizeof(long long) * total, s));
+    CU(cudaMemsetAsync(pl->err_dev.p, 0, sizeof(int), s));
+    const int cap = pick_kc(26, pl->tb);
+    for (uint32_t c0 = 0; c0 < kmax; c0 += cap) {
+        const int kc = pick_kc((int)std::min<uint32_t>(cap, kmax - c0), pl->tb);
+        SweepArgs a;
+        a.base_w = pl->w_dev.p;
+        a.fid = pl->fid_dev.p;
+        a.cand_w = pl->cand_dev.p;
+        a.n_cand = pl->ncand_dev.p;
+        a.sums = pl->sums_dev.p;
+        a.wlen = (uint32_t)wlen;
+        a.cand_stride = (uint32_t)cand_stride;
+        a.cand_off = c0;
+        a.err = pl->err_dev.p;
+        if (pl->nt > 0 && launch_sweep(pl, kc, pl->tb, (uint32_t)n_sweeps, a, s)) return 1;
+    }
+    if (allreduce_sums(pl, pl->sums_dev.p, total, s)) return 1;
+    CU(cudaMemcpyAsync(pl->sums_host.p, pl->sums_dev.p, sizeof(long long) * total,
+                       cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(pl->err_host.p, pl->err_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (check_err_flags(pl->err_host.p[0])) return 1;
+    for (size_t i = 0; i < total; ++i) out_sum_fx[i] = pl->sums_host.p[i];
+    return 0;
+}
+
+int fr_dev_model_create(fr_dev_dataset *ds, const uint64_t *code, size_t n_words, fr_dev_model **out) {
+    if (!out) return fail("fr_dev_model_create: out is NULL");
+    *out = nullptr;
+    if (!ds || !code || n_words == 0) return fail("fr_dev_model_create: NULL argument");
+    CU(cudaSetDevice(ds->device));
+    std::unique_ptr<fr_dev_model> m(new fr_dev_model());
+    m->ds = ds;
+    m->n_words = n_words;
+    CU(m->code.alloc(n_words));
+    CU(cudaMemcpy(m->code.p, code, sizeof(uint64_t) * n_words, cudaMemcpyHostToDevice));
+    *out = m.release();
+    return 0;
+}
+
+void fr_dev_model_destroy(fr_dev_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->ds->device);
+    delete m;
+}
+
+int fr_dev_score_model(fr_dev_dataset *ds, const fr_dev_model *m, double *out_scores) {
+    if (!ds || !m || !out_scores) return fail("fr_dev_score_model: NULL argument");
+    CU(cudaSetDevice(ds->device));
+    cudaStream_t s = ds->stream;
+    CU(ds->scores_inst.ensure(ds->n));
+    const int tb = 128;
+    model_score_kernel<<<(unsigned)((ds->n + tb - 1) / tb), tb, 0, s>>>(
+        ds->x.p, ds->ld, (uint32_t)ds->d, ds->n, m->code.p, ds->inst_of_pos_dev.p, nullptr,
+        ds->scores_inst.p);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_scores, ds->scores_inst.p, sizeof(double) * ds->n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int fr_dev_eval_model(fr_dev_plan *pl, const fr_dev_model *m, int64_t *out_sum_fx,
+                      double *out_per_query) {
+    if (!pl || !m || !out_sum_fx) return fail("fr_dev_eval_model: NULL argument");
+    fr_dev_dataset *ds = pl->ds;
+    CU(cudaSetDevice(ds->device));
+    cudaStream_t s = ds->stream;
+    CU(ds->scores_pos.ensure(ds->n));
+    CU(pl->sums_dev.ensure(1));
+    CU(pl->sums_host.ensure(1));
+    CU(cudaMemsetAsync(pl->sums_dev.p, 0, sizeof(long long), s));
+    CU(cudaMemsetAsync(pl->err_dev.p, 0, sizeof(int), s));
+    if (out_per_query) CU(pl->perq_dev.ensure(pl->nq_view));
+    const int tb = 128;
+    model_score_kernel<<<(unsigned)((ds->n + tb - 1) / tb), tb, 0, s>>>(
+        ds->x.p, ds->ld, (uint32_t)ds->d, ds->n, m->code.p, ds->inst_of_pos_dev.p, ds->scores_pos.p,
+        nullptr);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    if (pl->nt > 0 &&
+        launch_scores_eval(pl, ds->scores_pos.p, pl->sums_dev.p, out_per_query ? pl->perq_dev.p : nullptr,
+                           pl->err_dev.p, s))
+        return 1;
+    if (allreduce_sums(pl, pl->sums_dev.p, 1, s)) return 1;
+    CU(cudaMemcpyAsync(pl->sums_host.p, pl->sums_dev.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(pl->err_host.p, pl->err_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (out_per_query)
+        CU(cudaMemcpyAsync(out_per_query, pl->perq_dev.p, sizeof(double) * pl->nq_view,
+                           cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (check_err_flags(pl->err_host.p[0])) return 1;
+    out_sum_fx[0] = pl->sums_host.p[0];
+    return 0;
+}
+
+int fr_dev_timer_start(fr_dev_dataset *ds) {
+    if (!ds) return fail("fr_dev_timer_start: NULL dataset");
+    CU(cudaSetDevice(ds->device));
+    if (!ds->t0) CU(cudaEventCreate(&ds->t0));
+    if (!ds->t1) CU(cudaEventCreate(&ds->t1));
+    CU(cudaStreamSynchronize(ds->stream));
+    CU(cudaEventRecord(ds->t0, ds->stream));
+    return 0;
+}
+
+int fr_dev_timer_stop(fr_dev_dataset *ds, double *out_ms) {
+    if (!ds || !out_ms || !ds->t0) return fail("fr_dev_timer_stop: timer was not started");
+    CU(cudaSetDevice(ds->device));
+    CU(cudaEventRecord(ds->t1, ds->stream));
+    CU(cudaEventSynchronize(ds->t1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ds->t0, ds->t1));
+    *out_ms = (double)ms;
+    return 0;
+}
+
+int fr_dev_profile_enable(fr_dev_dataset *ds, int on) {
+    if (!ds) return fail("fr_dev_profile_enable: NULL dataset");
+    ds->profile = on != 0;
+    return 0;
+}
+
+int fr_dev_profile_read(fr_dev_dataset *ds, uint64_t *out_launches, double *out_total_ms, int reset) {
+    if (!ds || !out_launches || !out_total_ms) return fail("fr_dev_profile_read: NULL argument");
+    CU(cudaSetDevice(ds->device));
+    CU(cudaStreamSynchronize(ds->stream));
+    double total = 0.0;
+    for (size_t i = 0; i < ds->prof_used; ++i) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ds->prof_events[i].first, ds->prof_events[i].second));
+        total += (double)ms;
+    }
+    *out_launches = ds->prof_used;
+    *out_total_ms = total;
+    if (reset) ds->prof_used = 0;
+    return 0;
+}
+
+int fr_dev_comm_unique_id(uint8_t out_id[128]) {
+    NcclApi &api = nccl();
+    if (!api.ok) return fail(api.why);
+    NcclApi::UniqueId id;
+    int rc = api.GetUniqueId(&id);
+    if (rc != 0) return fail("ncclGetUniqueId failed");
+    memcpy(out_id, id.internal, 128);
+    return 0;
+}
+
+int fr_dev_comm_create(int device, int rank, int world, const uint8_t id[128], fr_dev_comm **out) {
+    if (!out) return fail("fr_dev_comm_create: out is NULL");
+    *out = nullptr;
+    NcclApi &api = nccl();
+    if (!api.ok) return fail(api.why);
+    CU(cudaSetDevice(device));
+    std::unique_ptr<fr_dev_comm> c(new fr_dev_comm());
+    c->device = device;
+    c->rank = rank;
+    c->world = world;
+    NcclApi::UniqueId uid;
+    memcpy(uid.internal, id, 128);
+    int rc = api.CommInitRank(&c->comm, world, uid, rank);
+    if (rc != 0)
+        return fail(std::string("ncclCommInitRank: ") + (api.GetErrorString ? api.GetErrorString(rc) : "?"));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c.release();
+    return 0;
+}
+
+void fr_dev_comm_destroy(fr_dev_comm *comm) {
+    if (!comm) return;
+    cudaSetDevice(comm->device);
+    if (comm->comm && nccl().ok) nccl().CommDestroy(comm->comm);
+    if (comm->stream) cudaStreamDestroy(comm->stream);
+    delete comm;
+}
+
+static std::atomic<fr_dev_comm *> g_default_comm{nullptr};
+void fr_dev_set_default_comm(fr_dev_comm *comm) { g_default_comm.store(comm); }
+fr_dev_comm *fr_dev_default_comm(void) { return g_default_comm.load(); }
+
+int fr_dev_comm_allreduce_u64(fr_dev_comm *comm, uint64_t *inout, size_t n) {
+    if (!comm || !inout) return fail("fr_dev_comm_allreduce_u64: NULL argument");
+    if (comm->world <= 1 || n == 0) return 0;
+    NcclApi &api = nccl();
+    if (!api.ok) return fail(api.why);
+    CU(cudaSetDevice(comm->device));
+    CU(comm->scratch.ensure(n));
+    CU(cudaMemcpyAsync(comm->scratch.p, inout, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, comm->stream));
+    int rc = api.AllReduce(comm->scratch.p, comm->scratch.p, n, kNcclUint64, kNcclSum, comm->comm,
+                           comm->stream);
+    if (rc != 0) return fail("ncclAllReduce failed");
+    CU(cudaMemcpyAsync(inout, comm->scratch.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, comm->stream));
+    CU(cudaStreamSynchronize(comm->stream));
+    return 0;
+}
+
+}  // extern "C"

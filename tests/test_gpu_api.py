@@ -1,0 +1,248 @@
+"""The reference's own integration tests (reference tests/test_with_example_data.py), restated
+against fastrank_b200's Python surface + C ABI on the GPU, plus oracle parity for scoring,
+tree ensembles and coordinate ascent end to end."""
+import json
+import os
+import tempfile
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from tests.helpers import oracle_dataset, synth
+
+pytestmark = pytest.mark.gpu
+
+_EXPECTED_N = 782
+_EXPECTED_D = 6
+_EXPECTED_FEATURE_NAMES = {"0", "pagerank", "para-fraction", "caption_count", "caption_partial", "caption_position"}
+
+
+@pytest.fixture(scope="module")
+def fr():
+    import fastrank_b200
+
+    return fastrank_b200
+
+
+@pytest.fixture(scope="module")
+def rd(fr, golden_dir):
+    return fr.CDataset.open_ranksvm(os.path.join(golden_dir, "trec_news_2018.train"),
+                                    os.path.join(golden_dir, "trec_news_2018.features.json"))
+
+
+@pytest.fixture(scope="module")
+def qrel(fr, golden_dir):
+    return fr.CQRel.load_file(os.path.join(golden_dir, "newsir18-entity.qrel"))
+
+
+@pytest.fixture(scope="module")
+def train_req(fr):
+    req = fr.TrainRequest.coordinate_ascent()
+    req.params.seed = 42
+    req.params.quiet = True
+    return req
+
+
+@pytest.fixture(scope="module")
+def model(rd, train_req):
+    return rd.train_model(train_req)
+
+
+def _single_feature_req(train_req):
+    req = train_req.clone()
+    lp = req.params
+    lp.num_restarts = 1
+    lp.num_max_iterations = 1
+    lp.step_base = 1.0
+    lp.normalize = False
+    lp.init_random = False
+    return req
+
+
+def test_single_feature_goldens(rd, train_req, goldens):
+    # reference tests/test_with_example_data.py:139-167
+    name_to_index = rd.feature_name_to_index()
+    req = _single_feature_req(train_req)
+    for feature in _EXPECTED_FEATURE_NAMES:
+        rd_single = rd.subsample_feature_names([feature])
+        m = rd_single.train_model(req)
+        got = np.mean(list(rd.evaluate(m, "ndcg@5").values()))
+        assert got == pytest.approx(goldens["single_feature_ndcg5"]["values"][feature], abs=1e-7)
+        for i, w in enumerate(m.to_dict()["Linear"]["weights"]):
+            if i != name_to_index[feature]:
+                assert w == pytest.approx(0.0, abs=1e-7)
+
+
+def test_subsample_queries_and_predict(rd, train_req, golden_dir):
+    # reference :106-137
+    subset = "378 363 811 321 807 347 646 397 802 804".split()
+    sample = rd.subsample_queries(subset)
+    assert sample.queries() == set(subset)
+    assert sample.num_features() == _EXPECTED_D
+    assert sample.feature_names() == _EXPECTED_FEATURE_NAMES
+    counts = Counter(line.split()[1][4:] for line in open(os.path.join(golden_dir, "trec_news_2018.train")))
+    assert sample.num_instances() == sum(counts[q] for q in subset)
+    m = sample.train_model(_single_feature_req(train_req))
+    sparse = m.predict_scores(sample)
+    assert len(sparse) == sample.num_instances()
+    dense = m.predict_dense_scores(sample)
+    assert len(dense) > len(sparse)
+    for ids in sample.instances_by_query().values():
+        for num in ids:
+            assert num < len(dense)
+    fast = m.predict_dense(sample)
+    for k, v in sparse.items():
+        assert fast[k] == v
+    assert np.isnan(fast).sum() == len(fast) - len(sparse)
+
+
+def test_train_model_beats_single_features(rd, model):
+    model._require_init()
+    got = np.mean(list(rd.evaluate(model, "ndcg@5").values()))
+    assert got >= 0.4394
+    assert rd.evaluate_mean(model, "ndcg@5") == pytest.approx(got, abs=1e-11)
+
+
+def test_model_serialization_roundtrip(fr, rd, model):
+    # reference :203-214
+    a = rd.evaluate(model, "map")
+    b = rd.evaluate(fr.CModel.from_dict(model.to_dict()), "map")
+    assert a.keys() == b.keys()
+    for k in a:
+        assert a[k] == b[k]
+
+
+def test_from_numpy(fr, train_req, golden_dir, oracle, trec_train):
+    # reference :216-241 (sklearn's zero_based=False loader drops column 0)
+    X = np.ascontiguousarray(trec_train.X[:, 1:])
+    y = trec_train.gains.astype(np.float64)
+    qid = np.asarray([int(q) for q in trec_train.qids], dtype=np.int64)
+    train = fr.CDataset.from_numpy(X, y, qid)
+    assert train.is_sampled() is False
+    assert train.num_features() == _EXPECTED_D - 1
+    assert train.num_instances() == _EXPECTED_N
+    assert train.feature_ids() == set(range(_EXPECTED_D - 1))
+    assert train.feature_names() == set(str(i) for i in range(_EXPECTED_D - 1))
+    assert len(train.queries()) == 45
+    m = train.train_model(train_req)
+    scores = m.predict_scores(train)
+    assert 0 in scores and len(scores) - 1 in scores and len(scores) == len(y)
+    w = m.to_dict()["Linear"]["weights"]
+    exp = oracle.score_linear(X, w)
+    assert [scores[i] for i in range(len(y))] == exp.tolist()
+
+
+def test_evaluate_with_and_without_qrel(rd, model, qrel):
+    # reference :243-251
+    a = np.mean(list(rd.evaluate(model, "ndcg@5", qrel).values()))
+    b = np.mean(list(rd.evaluate(model, "ndcg@5").values()))
+    assert abs(a - b) < 1e-7
+
+
+def test_sampled_evaluation(rd, model):
+    # reference :253-269
+    full = rd.evaluate(model, "ndcg@5")
+    first = sorted(full.keys())[:10]
+    partial = rd.subsample_queries(first)
+    assert partial.is_sampled() is True
+    assert len(partial.instances_by_query()) == 10
+    got = partial.evaluate(model, "ndcg@5")
+    assert len(got) == 10
+    for q in first:
+        assert got[q] == full[q]
+
+
+def test_trecrun_error_path(rd, model):
+    # reference :271-279
+    with tempfile.NamedTemporaryFile(mode="r") as tmpf:
+        with pytest.raises(Exception, match="Dataset does not contain document ids"):
+            rd.predict_trecrun(model, tmpf.name)
+
+
+def test_evaluate_every_measure_matches_oracle(fr, rd, qrel, oracle, trec_train, golden_dir):
+    rng = np.random.default_rng(21)
+    w = rng.normal(size=6).tolist()
+    m = fr.CModel.from_dict({"Linear": {"weights": w}})
+    qd = oracle.load_qrel(os.path.join(golden_dir, "newsir18-entity.qrel"))
+    for measure in ("ndcg", "ndcg@5", "NDCG@1", "map", "ap", "rr", "mrr"):
+        for use_qrel in (False, True):
+            got = rd.evaluate(m, measure, qrel if use_qrel else None)
+            exp = oracle.evaluate_model(trec_train, {"Linear": {"weights": w}}, measure, qd if use_qrel else None)
+            assert got == exp, (measure, use_qrel)
+
+
+def test_tree_ensemble_scores_bit_exact(fr, oracle):
+    X, y, qid = synth(4000, 12, 100, seed=31)
+    rng = np.random.default_rng(6)
+
+    def rand_tree(depth):
+        if depth == 0 or rng.random() < 0.15:
+            return {"LeafNode": float(rng.normal())}
+        fid = int(rng.integers(0, 14))        # ids 12, 13 are beyond the row: read as 0.0
+        col = X[:, fid] if fid < 12 else np.zeros(1)
+        split = float(rng.choice(col)) if rng.random() < 0.5 else float(np.quantile(col, rng.random()))
+        return {"FeatureSplit": {"fid": fid, "split": split, "lhs": rand_tree(depth - 1), "rhs": rand_tree(depth - 1)}}
+
+    trees = [{"DecisionTree": rand_tree(7)} for _ in range(40)]
+    ens = {"Ensemble": {"weights": [float(v) for v in rng.normal(size=40)], "models": trees}}
+    nested = {"Ensemble": {"weights": [0.5, -2.0, 1.0],
+                           "models": [ens, {"Linear": {"weights": [float(v) for v in rng.normal(size=12)]}},
+                                      {"SingleFeature": {"fid": 2, "dir": -1.0}}]}}
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    ods = oracle_dataset(oracle, X, y, qid)
+    for spec in (trees[0], ens, nested):
+        m = fr.CModel.from_dict(spec)
+        got = m.predict_dense(ds)
+        exp = oracle.score_model(X, spec)
+        assert np.array_equal(got, exp)
+        for measure in ("ndcg@10", "map"):
+            e = ds.evaluate(m, measure)
+            o = oracle.evaluate_model(ods, spec, measure)
+            assert e == o
+
+
+def test_coordinate_ascent_matches_oracle_run(fr, oracle, trec_train, rd, train_req):
+    # same RNG restatement on both sides: trajectories should coincide; the bar SURVEY 8c sets
+    # is the final training metric within 1e-3.
+    req = train_req.clone()
+    req.measure = "ndcg@5"
+    req.params.num_restarts = 3
+    m = rd.train_model(req)
+    res = oracle.coordinate_ascent(trec_train, "ndcg@5", num_restarts=3, seed=42)
+    got = rd.evaluate_mean(m, "ndcg@5")
+    assert abs(got - res["score"]) < 1e-3
+    w = np.asarray(m.to_dict()["Linear"]["weights"])
+    assert np.allclose(w, res["weights"], rtol=0, atol=1e-12)
+    stats = fr.query_json("last_train_stats")
+    assert stats["evals_consumed"] == res["n_evals"]
+    assert stats["evals_computed"] >= stats["evals_consumed"]
+
+
+def test_ca_on_synthetic_with_map_and_ensemble_output(fr, oracle):
+    X, y, qid = synth(3000, 8, 80, seed=41)
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    req = fr.TrainRequest.coordinate_ascent()
+    req.measure = "map"
+    req.params.seed = 7
+    req.params.quiet = True
+    req.params.num_restarts = 2
+    req.params.output_ensemble = True
+    m = ds.train_model(req)
+    spec = m.to_dict()
+    assert list(spec.keys()) == ["Ensemble"] and len(spec["Ensemble"]["models"]) == 2
+    ods = oracle_dataset(oracle, X, y, qid)
+    assert ds.evaluate(m, "map") == oracle.evaluate_model(ods, spec, "map")
+    res = oracle.coordinate_ascent(ods, "map", num_restarts=2, seed=7)
+    assert np.allclose(sorted(spec["Ensemble"]["weights"]), sorted(res["all_scores"]), atol=1e-12)
+
+
+def test_error_paths(fr, rd):
+    with pytest.raises(Exception, match="Invalid training measure"):
+        rd.evaluate(fr.CModel.from_dict({"Linear": {"weights": [1.0]}}), "bogus")
+    with pytest.raises(Exception, match="parse after the @"):
+        rd.evaluate(fr.CModel.from_dict({"Linear": {"weights": [1.0]}}), "ndcg@x")
+    req = fr.TrainRequest.random_forest()
+    req.params.quiet = True
+    with pytest.raises(Exception):
+        rd.subsample_feature_names(["nope"])

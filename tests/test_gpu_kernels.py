@@ -1,0 +1,200 @@
+"""Parity of the CUDA kernels (through the fr_dev_* C ABI) against the CPU oracle:
+per-query metric values bit-exact, fixed-point sums exactly equal."""
+import numpy as np
+import pytest
+
+from tests.helpers import DevDataset, dense_qidx, fx_sum, oracle_dataset, synth
+
+pytestmark = pytest.mark.gpu
+
+METRICS = [("ndcg@10", 0, 10), ("ndcg", 0, -1), ("ndcg@3", 0, 3), ("map", 1, -1), ("rr", 2, -1)]
+
+
+def _mk(oracle, n, d, q, seed, shuffle=False):
+    X, y, qid = synth(n, d, q, seed=seed, shuffle_rows=shuffle)
+    ods = oracle_dataset(oracle, X, y, qid)
+    qidx, nq = dense_qidx(qid)
+    dev = DevDataset(X, y.astype(np.float32), qidx, nq)
+    return X, y, qid, ods, dev
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_linear_batch_bit_exact(oracle, shuffle):
+    X, y, qid, ods, dev = _mk(oracle, 6000, 24, 180, seed=3, shuffle=shuffle)
+    rng = np.random.default_rng(0)
+    W = rng.normal(size=(11, 24))
+    W[3, :] = 0.0                      # all scores tie -> pure tie-break order
+    W[4, :] = 0.0
+    W[4, 2] = 1.0                      # integer column: heavy ties
+    try:
+        for name, metric, depth in METRICS:
+            plan = dev.plan(metric, depth)
+            sums, pq = plan.eval_linear(W)
+            for c in range(W.shape[0]):
+                exp = oracle.evaluate_scores(ods, oracle.score_linear(X, W[c]), name)
+                assert np.array_equal(pq[c], exp), (name, c, np.abs(pq[c] - exp).max())
+                assert int(sums[c]) == fx_sum(exp)
+    finally:
+        dev.close()
+
+
+def test_ragged_and_long_queries(oracle):
+    # query lengths 1 .. ~700 in one dataset: exercises every tile size up to 1024
+    rng = np.random.default_rng(9)
+    lens = [1, 2, 3, 31, 32, 33, 64, 127, 128, 129, 255, 257, 600, 700, 5, 1]
+    qid = np.concatenate([np.full(l, 100 + i) for i, l in enumerate(lens)]).astype(np.int64)
+    n = len(qid)
+    X = rng.normal(size=(n, 7)).astype(np.float32)
+    X[:, 3] = rng.integers(0, 3, n)
+    y = rng.integers(0, 5, n).astype(np.float64)
+    y[qid == 102] = 0.0                 # a query without relevant documents
+    ods = oracle_dataset(oracle, X, y, qid)
+    qidx, nq = dense_qidx(qid)
+    dev = DevDataset(X, y.astype(np.float32), qidx, nq)
+    W = rng.normal(size=(5, 7))
+    W[1, :] = 0
+    W[1, 3] = -1.0
+    try:
+        for name, metric, depth in METRICS:
+            plan = dev.plan(metric, depth)
+            sums, pq = plan.eval_linear(W)
+            for c in range(W.shape[0]):
+                exp = oracle.evaluate_scores(ods, oracle.score_linear(X, W[c]), name)
+                assert np.array_equal(pq[c], exp), (name, c)
+                assert int(sums[c]) == fx_sum(exp)
+    finally:
+        dev.close()
+
+
+def test_negative_and_fractional_gains(oracle):
+    rng = np.random.default_rng(4)
+    n = 900
+    qid = np.sort(rng.integers(0, 40, n)).astype(np.int64)
+    X = rng.normal(size=(n, 5)).astype(np.float32)
+    y = rng.choice([-1.0, 0.0, 0.5, 1.0, 2.5], size=n)
+    ods = oracle_dataset(oracle, X, y, qid)
+    qidx, nq = dense_qidx(qid)
+    dev = DevDataset(X, y.astype(np.float32), qidx, nq)
+    W = rng.normal(size=(3, 5))
+    try:
+        for name, metric, depth in METRICS:
+            plan = dev.plan(metric, depth)
+            sums, pq = plan.eval_linear(W)
+            for c in range(3):
+                exp = oracle.evaluate_scores(ods, oracle.score_linear(X, W[c]), name)
+                assert np.array_equal(pq[c], exp), (name, c)
+                assert int(sums[c]) == fx_sum(exp)
+    finally:
+        dev.close()
+
+
+def test_weight_vector_length_truncation(oracle):
+    # zip() truncation (dense_dataset.rs:72): shorter and longer weight vectors than D
+    X, y, qid, ods, dev = _mk(oracle, 1500, 9, 50, seed=5)
+    rng = np.random.default_rng(1)
+    try:
+        plan = dev.plan(0, 5)
+        for wlen in (4, 9, 13):
+            W = rng.normal(size=(2, wlen))
+            sums, pq = plan.eval_linear(W)
+            for c in range(2):
+                exp = oracle.evaluate_scores(ods, oracle.score_linear(X, W[c]), "ndcg@5")
+                assert np.array_equal(pq[c], exp)
+    finally:
+        dev.close()
+
+
+@pytest.mark.parametrize("ncand", [1, 2, 5, 26, 51])
+def test_coord_sweeps_match_full_rescoring(oracle, ncand):
+    X, y, qid, ods, dev = _mk(oracle, 5000, 20, 150, seed=7)
+    rng = np.random.default_rng(ncand)
+    base = rng.normal(size=(4, 20))
+    base[2, 5] = 0.0
+    fids = [0, 19, 5, 10]
+    cands = []
+    for r in range(4):
+        orig = base[r, fids[r]]
+        c = [0.0] + [orig + s * 0.05 * (2.0 ** k - 1) for k in range(1, 40) for s in (-1, 1)]
+        cands.append(c[:ncand])
+    try:
+        for name, metric, depth in [("ndcg@10", 0, 10), ("map", 1, -1)]:
+            plan = dev.plan(metric, depth)
+            sums = plan.coord_sweeps(base, fids, cands)
+            for r in range(4):
+                for k, wv in enumerate(cands[r]):
+                    w = base[r].copy()
+                    w[fids[r]] = wv
+                    exp = oracle.evaluate_scores(ods, oracle.score_linear(X, w), name)
+                    assert int(sums[r, k]) == fx_sum(exp), (name, r, k)
+    finally:
+        dev.close()
+
+
+def test_coord_sweep_feature_beyond_row(oracle):
+    # model_dim can exceed D for a Linear model loaded from JSON; the extra weight is inert
+    X, y, qid, ods, dev = _mk(oracle, 800, 6, 30, seed=8)
+    base = np.random.default_rng(2).normal(size=(1, 9))
+    try:
+        plan = dev.plan(0, 10)
+        sums = plan.coord_sweeps(base, [7], [[0.0, 1.0, -3.0]])
+        exp = oracle.evaluate_scores(ods, oracle.score_linear(X, base[0]), "ndcg@10")
+        assert [int(v) for v in sums[0]] == [fx_sum(exp)] * 3
+    finally:
+        dev.close()
+
+
+def test_query_and_instance_subsets(oracle):
+    X, y, qid, ods, dev = _mk(oracle, 3000, 10, 90, seed=11)
+    rng = np.random.default_rng(3)
+    W = rng.normal(size=(2, 10))
+    names = ods.query_names
+    pick = [5, 17, 3, 60]
+    try:
+        # query subset
+        plan = dev.plan(0, 5, query_ids=pick)
+        sums, pq = plan.eval_linear(W)
+        ods.set_view([names[i] for i in pick])
+        for c in range(2):
+            exp = oracle.evaluate_scores(ods, oracle.score_linear(X, W[c]), "ndcg@5")
+            assert np.array_equal(pq[c], exp)
+        # instance subset inside those queries
+        keep, offs = [], [0]
+        for i in pick:
+            ids = ods.by_query[names[i]]
+            sub = ids[::2]
+            keep.extend(sub)
+            offs.append(len(keep))
+        plan2 = dev.plan(1, -1, query_ids=pick, inst=(offs, keep))
+        sums2, pq2 = plan2.eval_linear(W)
+        ods.set_view([names[i] for i in pick], instances=keep)
+        for c in range(2):
+            exp = oracle.evaluate_scores(ods, oracle.score_linear(X, W[c]), "map")
+            assert np.array_equal(pq2[c], exp)
+    finally:
+        ods.set_view(names)
+        dev.close()
+
+
+def test_nan_score_is_reported(oracle):
+    X, y, qid, ods, dev = _mk(oracle, 300, 4, 10, seed=12)
+    try:
+        plan = dev.plan(0, 5)
+        W = np.array([[np.nan, 0.0, 0.0, 0.0]])
+        with pytest.raises(RuntimeError, match="NaN"):
+            plan.eval_linear(W)
+    finally:
+        dev.close()
+
+
+def test_fixed_point_sum_is_geometry_independent(oracle):
+    # the same queries in a different order (different tiling) give the same integer sum
+    X, y, qid, ods, dev = _mk(oracle, 4000, 8, 120, seed=13)
+    rng = np.random.default_rng(5)
+    W = rng.normal(size=(3, 8))
+    try:
+        a, _ = dev.plan(0, 10).eval_linear(W, per_query=False)
+        perm = rng.permutation(120)
+        b, _ = dev.plan(0, 10, query_ids=perm).eval_linear(W, per_query=False)
+        assert a.tolist() == b.tolist()
+    finally:
+        dev.close()
