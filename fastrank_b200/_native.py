@@ -45,7 +45,7 @@ ffi = cffi.FFI()
 ffi.cdef(header_cdef())
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        "fastrank_b200: %s is missing -- build it with `python -m fastrank_b200.build` "
+        "fastrank_b200: %s is missing -- build it with `python fastrank_b200/build.py` "
         "(there is no CPU fallback)" % LIB_PATH
     )
 lib = ffi.dlopen(LIB_PATH)

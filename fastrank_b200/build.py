@@ -2,7 +2,7 @@
 host, one shared object with cudart linked statically (so it loads on a machine without a
 GPU and reports the missing device at call time).
 
-    python -m fastrank_b200.build [--force]
+    python fastrank_b200/build.py [--force]
 """
 from __future__ import annotations
 
