@@ -20,6 +20,7 @@ class DevDataset:
         self.gains = np.ascontiguousarray(gains, dtype=np.float32)
         self.qidx = np.ascontiguousarray(qidx, dtype=np.uint32)
         self.nq = int(nq)
+        ffi, lib = _ffi, _lib
         out = ffi.new("fr_dev_dataset**")
         rc = lib.fr_dev_dataset_create(device, self.X.shape[0], self.X.shape[1],
                                        ffi.cast("float*", self.X.ctypes.data),
