@@ -261,8 +261,8 @@ def run_ours(args, rank, world, local_rank):
 
     def one_step(s):
         base, fids, ga, gb = step_inputs(s, d)
-        plan.coord_sweeps(base, fids, ga)
-        plan.coord_sweeps(base, fids, gb)
+        plan.coord_sweeps(base, fids, ga, fast=not args.exact)
+        plan.coord_sweeps(base, fids, gb, fast=not args.exact)
 
     for s in range(args.warmup):
         one_step(s)
@@ -368,6 +368,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exact", action="store_true", help="time the exact-order sweep kernel instead of the batched one")
     ap.add_argument("--cpu-evals-per-thread", type=int, default=4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

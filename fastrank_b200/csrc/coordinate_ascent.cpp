@@ -15,6 +15,7 @@
 // apart.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "host.hpp"
@@ -132,6 +133,9 @@ Model coordinate_ascent_learn(const CoordinateAscentParams &p, const DatasetView
 
     const size_t T = p.num_max_iterations;
     const size_t stride = 1 + T;
+    bool use_fast = fr_dev_plan_has_fast_sweep(ev.plan()) != 0;
+    if (const char *env = getenv("FASTRANK_SWEEP"))
+        if (std::string(env) == "exact") use_fast = false;
     std::vector<double> base_w, cand_w;
     std::vector<uint32_t> fid_arr, ncand;
     std::vector<int64_t> sums;
@@ -177,11 +181,17 @@ Model coordinate_ascent_learn(const CoordinateAscentParams &p, const DatasetView
             ncand[a] = (uint32_t)r.cands.size();
             stats.evals_computed += r.cands.size();
         }
-        // 2. one GPU pass per restart
+        // 2. one GPU pass over the feature matrix for all restarts (batched sweep); the
+        //    exact-order kernel (one pass per restart) on request or for very long queries
         sums.assign(active.size() * stride, 0);
-        if (fr_dev_eval_coord_sweeps(ev.plan(), active.size(), base_w.data(), dim, fid_arr.data(),
-                                     cand_w.data(), ncand.data(), stride, sums.data()))
-            throw Error(fr_dev_last_error());
+        const int rc = use_fast
+                           ? fr_dev_eval_coord_sweeps_fast(ev.plan(), active.size(), base_w.data(), dim,
+                                                           fid_arr.data(), cand_w.data(), ncand.data(),
+                                                           stride, sums.data(), nullptr)
+                           : fr_dev_eval_coord_sweeps(ev.plan(), active.size(), base_w.data(), dim,
+                                                      fid_arr.data(), cand_w.data(), ncand.data(), stride,
+                                                      sums.data());
+        if (rc) throw Error(fr_dev_last_error());
         stats.sweeps += active.size();
         stats.global_steps += 1;
         // 3. replay the reference's sequential control flow on the means

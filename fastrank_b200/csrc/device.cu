@@ -20,272 +20,13 @@
 // Determinism: per-query metric values are bit-identical to the oracle; they are summed as
 // signed fixed point (2^-40) with integer atomics, so the mean does not depend on launch
 // geometry, atomics order or the number of GPUs.
-#include <cuda_runtime.h>
-#include <dlfcn.h>
-
-#include <algorithm>
-#include <atomic>
-#include <climits>
-#include <cmath>
-#include <cstdint>
-#include <cstdio>
-#include <cstring>
-#include <map>
-#include <memory>
-#include <mutex>
-#include <string>
-#include <vector>
-
-#include "../../include/fastrank_b200.h"
-#include "model_program.hpp"
-
-namespace {
-
-thread_local std::string g_last_error;
-std::atomic<uint64_t> g_kernel_launches{0};
-
-int fail(const std::string &msg) {
-    g_last_error = msg;
-    return 1;
-}
-
-#define CU(expr)                                                                          \
-    do {                                                                                  \
-        cudaError_t e__ = (expr);                                                         \
-        if (e__ != cudaSuccess)                                                           \
-            return fail(std::string(#expr) + " failed: " + cudaGetErrorString(e__));      \
-    } while (0)
-
-#define LAUNCHED() g_kernel_launches.fetch_add(1, std::memory_order_relaxed)
-
-template <typename T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-    ~DevBuf() { release(); }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        n = 0;
-    }
-    cudaError_t alloc(size_t count) {
-        release();
-        n = count;
-        return cudaMalloc((void **)&p, sizeof(T) * (count ? count : 1));
-    }
-    cudaError_t upload(const std::vector<T> &h, cudaStream_t s = 0) {
-        cudaError_t e = alloc(h.size());
-        if (e != cudaSuccess || h.empty()) return e;
-        return cudaMemcpyAsync(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, s);
-    }
-    cudaError_t ensure(size_t count) { return count <= n && p ? cudaSuccess : alloc(count); }
-};
-
-template <typename T>
-struct PinnedBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    ~PinnedBuf() {
-        if (p) cudaFreeHost(p);
-    }
-    cudaError_t ensure(size_t count) {
-        if (count <= n && p) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        n = count;
-        return cudaMallocHost((void **)&p, sizeof(T) * (count ? count : 1));
-    }
-};
-
-constexpr int kMaxTile = 1024;
-constexpr double kFxScale = 1099511627776.0; /* 2^FR_FX_BITS */
-static_assert(FR_FX_BITS == 40, "kFxScale must match FR_FX_BITS");
-
-// ---------------------------------------------------------------------------------------
-// NCCL, bound at run time so the library loads on machines without it.
-// ---------------------------------------------------------------------------------------
-struct NcclApi {
-    typedef struct {
-        char internal[128];
-    } UniqueId;
-    int (*GetUniqueId)(UniqueId *) = nullptr;
-    int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
-    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
-    int (*CommDestroy)(void *) = nullptr;
-    const char *(*GetErrorString)(int) = nullptr;
-    bool ok = false;
-    std::string why;
-};
-
-NcclApi &nccl() {
-    static NcclApi api;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        const char *names[] = {"libnccl.so.2", "libnccl.so"};
-        void *h = nullptr;
-        for (const char *nm : names) {
-            h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-            if (h) break;
-        }
-        if (!h) {
-            const char *env = getenv("FASTRANK_NCCL_LIB");
-            if (env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
-        }
-        if (!h) {
-            api.why = "libnccl.so.2 not found (import torch first or set FASTRANK_NCCL_LIB)";
-            return;
-        }
-        api.GetUniqueId = (int (*)(NcclApi::UniqueId *))dlsym(h, "ncclGetUniqueId");
-        api.CommInitRank =
-            (int (*)(void **, int, NcclApi::UniqueId, int))dlsym(h, "ncclCommInitRank");
-        api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *,
-                                 cudaStream_t))dlsym(h, "ncclAllReduce");
-        api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
-        api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
-        api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
-        if (!api.ok) api.why = "libnccl is missing expected symbols";
-    });
-    return api;
-}
-constexpr int kNcclInt64 = 4;
-constexpr int kNcclUint64 = 5;
-constexpr int kNcclSum = 0;
-
-}  // namespace
-
-struct fr_dev_comm {
-    int device = 0;
-    int rank = 0;
-    int world = 1;
-    void *comm = nullptr;
-    cudaStream_t stream = nullptr;
-    DevBuf<uint64_t> scratch;
-};
-
-struct fr_dev_dataset {
-    int device = 0;
-    size_t n = 0, d = 0, ld = 0;
-    uint32_t nq = 0;
-    DevBuf<float> x;        // [d][ld]
-    DevBuf<float> gain;     // [n] by position
-    DevBuf<double> gexp;    // [n] by position
-    DevBuf<uint32_t> inst_of_pos_dev;
-    std::vector<uint32_t> inst_of_pos, pos_of_inst;
-    std::vector<uint32_t> q_start, q_len;  // per query, in positions
-    std::vector<float> gain_pos;           // host copy, by position
-    cudaStream_t stream = nullptr;
-    DevBuf<double> scores_pos;   // scratch for model scoring
-    DevBuf<double> scores_inst;  // scratch for predict
-    // device-side timing (fr_dev_timer_*, fr_dev_profile_*)
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    bool profile = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
-    size_t prof_used = 0;
-    ~fr_dev_dataset() {
-        for (auto &pr : prof_events) {
-            cudaEventDestroy(pr.first);
-            cudaEventDestroy(pr.second);
-        }
-        if (t0) cudaEventDestroy(t0);
-        if (t1) cudaEventDestroy(t1);
-        if (stream) cudaStreamDestroy(stream);
-    }
-    // event pair bracketing one kernel launch while profiling is on
-    std::pair<cudaEvent_t, cudaEvent_t> *prof_slot() {
-        if (!profile) return nullptr;
-        if (prof_used == prof_events.size()) {
-            cudaEvent_t a, b;
-            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return nullptr;
-            prof_events.emplace_back(a, b);
-        }
-        return &prof_events[prof_used++];
-    }
-};
-
-struct fr_dev_model {
-    fr_dev_dataset *ds = nullptr;
-    DevBuf<uint64_t> code;
-    size_t n_words = 0;
-};
-
-// Device-side view of a plan (passed to kernels by value).
-struct PlanView {
-    const float *x;
-    size_t ld;
-    uint32_t dfeat;
-    const float *gain;
-    const double *gexp;
-    const double *lg2;           // log2(i + 2)
-    const uint32_t *tile_doc_off;  // nt + 1
-    const uint32_t *tile_q_off;    // nt + 1
-    const uint32_t *pd_pos;        // plan doc -> position
-    const uint32_t *pd_q;          // plan doc -> (local query start) | (local query end << 16)
-    const uint32_t *pq_local;      // plan query -> (local start) | (len << 16)
-    const uint32_t *pq_doc0;       // plan query -> first plan doc
-    const double *pq_norm;         // ideal DCG (NaN = none) or num_relevant
-    const uint32_t *pq_view;       // plan query -> view (output) index
-    uint32_t nt;
-    uint32_t nq_plan;
-    uint32_t nq_view;
-    int metric;
-    int depth;  // INT_MAX when absent
-};
-
-struct fr_dev_plan {
-    fr_dev_dataset *ds = nullptr;
-    int metric = 0;
-    int depth = INT_MAX;
-    int tb = 128;
-    uint32_t nq_view = 0, nq_plan = 0, nt = 0;
-    uint32_t max_len = 0;
-    DevBuf<double> lg2;
-    DevBuf<uint32_t> tile_doc_off, tile_q_off, pd_pos, pd_q, pq_local, pq_doc0, pq_view;
-    DevBuf<double> pq_norm;
-    // work buffers
-    DevBuf<double> w_dev, cand_dev, perq_dev;
-    DevBuf<uint32_t> fid_dev, ncand_dev;
-    DevBuf<long long> sums_dev;
-    DevBuf<int> err_dev;
-    PinnedBuf<long long> sums_host;
-    PinnedBuf<int> err_host;
-    fr_dev_comm *comm = nullptr;
-    uint64_t nq_global = 0;
-    int sm_count = 148;
-    PlanView view() const {
-        PlanView v;
-        v.x = ds->x.p;
-        v.ld = ds->ld;
-        v.dfeat = (uint32_t)ds->d;
-        v.gain = ds->gain.p;
-        v.gexp = ds->gexp.p;
-        v.lg2 = lg2.p;
-        v.tile_doc_off = tile_doc_off.p;
-        v.tile_q_off = tile_q_off.p;
-        v.pd_pos = pd_pos.p;
-        v.pd_q = pd_q.p;
-        v.pq_local = pq_local.p;
-        v.pq_doc0 = pq_doc0.p;
-        v.pq_norm = pq_norm.p;
-        v.pq_view = pq_view.p;
-        v.nt = nt;
-        v.nq_plan = nq_plan;
-        v.nq_view = nq_view;
-        v.metric = metric;
-        v.depth = depth;
-        return v;
-    }
-};
+#include "device_common.cuh"
 
 // =========================================================================================
 // Kernels
 // =========================================================================================
 namespace {
 
-constexpr int ERR_NAN_SCORE = 1;
-constexpr int ERR_DCG_ABOVE_IDEAL = 2;
 
 // Rows of the host matrix -> feature-major, regrouped by query.
 __global__ void gather_transpose_kernel(const float *__restrict__ src,
@@ -794,6 +535,9 @@ int launch_scores_eval(fr_dev_plan *pl, const double *scores, long long *sums, d
     return 0;
 }
 
+}  // namespace
+
+namespace frbdev {
 int check_err_flags(int flags) {
     if (flags & ERR_NAN_SCORE) return fail("Model.predict -> NaN (a score was NaN)");
     if (flags & ERR_DCG_ABOVE_IDEAL)
@@ -812,7 +556,7 @@ int allreduce_sums(fr_dev_plan *pl, long long *dev, size_t count, cudaStream_t s
     return 0;
 }
 
-}  // namespace
+}  // namespace frbdev
 
 // =========================================================================================
 // C ABI
@@ -1025,6 +769,7 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
         LAUNCHED();
         CU(cudaGetLastError());
     }
+    if (build_fast_plan(pl.get(), tile_q_off, pq_local, pq_doc0, pd_pos)) return 1;
     CU(cudaStreamSynchronize(s));
     pl->nq_global = pl->nq_view;
     *out = pl.release();

@@ -125,8 +125,10 @@ class DevPlan:
         self.ds._check(rc)
         return sums, pq
 
-    def coord_sweeps(self, base_w: np.ndarray, fids, cands):
-        """cands: list (one per sweep) of candidate-weight lists."""
+    def coord_sweeps(self, base_w: np.ndarray, fids, cands, fast: bool = False, per_query: bool = False):
+        """cands: list (one per sweep) of candidate-weight lists.  fast=True calls the batched
+        sweep (fr_dev_eval_coord_sweeps_fast); per_query (fast only) also returns
+        [sweep][candidate][query] values."""
         ffi, lib = self.ds.ffi, self.ds.lib
         base_w = np.ascontiguousarray(base_w, dtype=np.float64)
         r, wlen = base_w.shape
@@ -138,6 +140,16 @@ class DevPlan:
             nc[i] = len(c)
         fid = np.ascontiguousarray(fids, dtype=np.uint32)
         sums = np.zeros((r, stride), dtype=np.int64)
+        if fast:
+            pq = np.zeros((r, stride, self.nq), dtype=np.float64) if per_query else None
+            rc = lib.fr_dev_eval_coord_sweeps_fast(self.ptr, r, ffi.cast("double*", base_w.ctypes.data), wlen,
+                                                   ffi.cast("uint32_t*", fid.ctypes.data),
+                                                   ffi.cast("double*", cw.ctypes.data),
+                                                   ffi.cast("uint32_t*", nc.ctypes.data), stride,
+                                                   ffi.cast("int64_t*", sums.ctypes.data),
+                                                   ffi.cast("double*", pq.ctypes.data) if per_query else ffi.NULL)
+            self.ds._check(rc)
+            return (sums, pq) if per_query else sums
         rc = lib.fr_dev_eval_coord_sweeps(self.ptr, r, ffi.cast("double*", base_w.ctypes.data), wlen,
                                           ffi.cast("uint32_t*", fid.ctypes.data),
                                           ffi.cast("double*", cw.ctypes.data),

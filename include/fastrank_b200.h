@@ -175,6 +175,20 @@ int fr_dev_eval_coord_sweeps(fr_dev_plan *plan, size_t n_sweeps, const double *b
                              const uint32_t *fid, const double *cand_w, const uint32_t *n_cand,
                              size_t cand_stride, int64_t *out_sum_fx);
 
+/* The same line searches, batched: ONE pass over the feature matrix serves every sweep of the
+ * call (groups of 8), candidates are scored as (prefix + x_f * cand) + suffix -- the reference's
+ * running sum up to coordinate f, then one pre-summed suffix (one rounding away from the
+ * reference's left-to-right order, ~1e-16 relative) -- and ranking, tie-break, metric terms and
+ * their summation order are the reference's.  Per-query values are bit-identical to the exact
+ * path whenever the ranking is.  This is what train_model uses (FASTRANK_SWEEP=exact selects
+ * the entry point above instead).  out_per_query: NULL or n_sweeps x cand_stride x n_queries. */
+int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *plan, size_t n_sweeps, const double *base_w,
+                                  size_t wlen, const uint32_t *fid, const double *cand_w,
+                                  const uint32_t *n_cand, size_t cand_stride, int64_t *out_sum_fx,
+                                  double *out_per_query);
+/* 1 when the batched sweep supports this plan (queries of at most 256 documents). */
+int fr_dev_plan_has_fast_sweep(const fr_dev_plan *plan);
+
 /* Flattened ModelEnum (model.rs:10-16).  `code` is a postfix program of 64-bit words; see
  * fastrank_b200/csrc/model_program.hpp for the encoding produced by the host. */
 int fr_dev_model_create(fr_dev_dataset *ds, const uint64_t *code, size_t n_words,

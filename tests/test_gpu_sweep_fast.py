@@ -1,0 +1,237 @@
+"""Parity of the batched coordinate-ascent sweep (fr_dev_eval_coord_sweeps_fast) against the
+CPU oracle and against the exact-order kernel.
+
+Contract under test (include/fastrank_b200.h): candidate scores are one rounding away from the
+reference's left-to-right dot product, everything after the score (ranking, tie-break, metric
+terms, summation order) is the reference's.  So:
+  * whenever the arithmetic is exact (dyadic weights on small-integer features, all-zero bases)
+    results must be BIT-IDENTICAL to the oracle, ties included;
+  * on generic float data per-query values are bit-identical wherever the ranking is, i.e.
+    everywhere except for documents whose scores agree to the last bits; the mean must be
+    within 1e-9 of the oracle (north_star tolerance: 1e-5).
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import DevDataset, dense_qidx, fx_sum, oracle_dataset, synth
+
+pytestmark = pytest.mark.gpu
+
+FX = float(1 << 40)
+
+
+def _mk(oracle, n, d, q, seed, shuffle=False, X=None, y=None, qid=None):
+    if X is None:
+        X, y, qid = synth(n, d, q, seed=seed, shuffle_rows=shuffle)
+    ods = oracle_dataset(oracle, X, y, qid)
+    qidx, nq = dense_qidx(qid)
+    dev = DevDataset(X, y.astype(np.float32), qidx, nq)
+    return X, y, qid, ods, dev
+
+
+def _line(orig, n):
+    c = [0.0] + [orig + s * 0.05 * (2.0 ** k - 1) for k in range(1, 40) for s in (-1, 1)]
+    return c[:n]
+
+
+def _check(oracle, ods, X, plan, name, base, fids, cands, exact=False, max_flip_frac=2e-4):
+    sums, pq = plan.coord_sweeps(base, fids, cands, fast=True, per_query=True)
+    nq = pq.shape[2]
+    total = flips = 0
+    for r in range(len(fids)):
+        for k, wv in enumerate(cands[r]):
+            w = base[r].copy()
+            if fids[r] < len(w):
+                w[fids[r]] = wv
+            exp = oracle.evaluate_scores(ods, oracle.score_linear(X, w), name)
+            got = pq[r, k]
+            bad = int((got != exp).sum())
+            total += nq
+            flips += bad
+            assert int(sums[r, k]) == fx_sum(got), "sum is not the sum of the per-query values"
+            if exact:
+                assert bad == 0, (name, r, k, np.abs(got - exp).max())
+                assert int(sums[r, k]) == fx_sum(exp)
+            else:
+                assert abs(got.mean() - exp.mean()) < 1e-9, (name, r, k)
+    assert flips <= max_flip_frac * total, (name, flips, total)
+    return flips, total
+
+
+@pytest.mark.parametrize("n_sweeps,ncand", [(1, 1), (3, 5), (8, 26), (8, 25), (11, 32), (2, 51)])
+def test_fast_sweeps_match_oracle(oracle, n_sweeps, ncand):
+    X, y, qid, ods, dev = _mk(oracle, 5000, 20, 150, seed=7)
+    rng = np.random.default_rng(100 * n_sweeps + ncand)
+    base = rng.normal(size=(n_sweeps, 20))
+    base /= np.abs(base).sum(axis=1, keepdims=True)
+    fids = [int(v) for v in rng.integers(0, 20, n_sweeps)]
+    fids[0] = 0
+    fids[-1] = 19
+    if n_sweeps > 2:
+        fids[1] = fids[2]  # two sweeps on the same coordinate
+    cands = [_line(base[r, fids[r]], ncand) for r in range(n_sweeps)]
+    try:
+        for name, metric, depth in [("ndcg@10", 0, 10), ("ndcg", 0, -1), ("map", 1, -1), ("rr", 2, -1)]:
+            plan = dev.plan(metric, depth)
+            assert dev.lib.fr_dev_plan_has_fast_sweep(plan.ptr) == 1
+            _check(oracle, ods, X, plan, name, base, fids, cands)
+    finally:
+        dev.close()
+
+
+def test_fast_sweeps_equal_exact_kernel_on_larger_data(oracle):
+    X, y, qid, ods, dev = _mk(oracle, 60000, 48, 1800, seed=21)
+    rng = np.random.default_rng(4)
+    base = rng.uniform(-1, 1, size=(8, 48))
+    base /= np.abs(base).sum(axis=1, keepdims=True)
+    fids = [int(v) for v in rng.integers(0, 48, 8)]
+    cands = [_line(base[r, fids[r]], 26) for r in range(8)]
+    try:
+        plan = dev.plan(0, 10)
+        exact = plan.coord_sweeps(base, fids, cands)
+        fast = plan.coord_sweeps(base, fids, cands, fast=True)
+        diff = np.abs(exact - fast).astype(np.float64) / FX / 1800
+        assert diff.max() < 1e-9, diff.max()
+        assert (exact == fast).mean() > 0.95
+    finally:
+        dev.close()
+
+
+def test_exact_arithmetic_cases_are_bit_identical(oracle):
+    """Small-integer features with dyadic weights: every product and sum is exact, so the fast
+    path must reproduce the oracle bit for bit -- including massive score ties, where only the
+    (gain asc, id asc) tie-break decides the ranking."""
+    rng = np.random.default_rng(5)
+    n, d, q = 4000, 12, 100
+    qid = np.sort(rng.integers(0, q, n)).astype(np.int64)
+    X = rng.integers(0, 4, size=(n, d)).astype(np.float32)
+    y = rng.integers(0, 5, n).astype(np.float64)
+    X, y, qid, ods, dev = _mk(oracle, n, d, q, 0, X=X, y=y, qid=qid)
+    base = rng.integers(-4, 5, size=(8, d)) / 8.0
+    base[0, :] = 0.0  # all scores tie for candidate 0.0
+    base[1, :] = 0.0
+    fids = [3, 0, 11, 5, 5, 7, 1, 2]
+    cands = [[0.0, 0.5, -0.25, 1.0, 2.0, -8.0, 0.125, 16.0] for _ in range(8)]
+    try:
+        for name, metric, depth in [("ndcg@10", 0, 10), ("ndcg@3", 0, 3), ("ndcg", 0, -1), ("map", 1, -1), ("rr", 2, -1)]:
+            plan = dev.plan(metric, depth)
+            _check(oracle, ods, X, plan, name, base, fids, cands, exact=True)
+    finally:
+        dev.close()
+
+
+def test_ragged_queries_and_length_limit(oracle):
+    rng = np.random.default_rng(9)
+    lens = [1, 2, 3, 31, 32, 33, 64, 127, 128, 129, 255, 256, 5, 1, 40]
+    qid = np.concatenate([np.full(l, 100 + i) for i, l in enumerate(lens)]).astype(np.int64)
+    n = len(qid)
+    X = rng.integers(0, 3, size=(n, 7)).astype(np.float32)
+    y = rng.integers(0, 5, n).astype(np.float64)
+    y[qid == 102] = 0.0  # a query without relevant documents
+    X, y, qid, ods, dev = _mk(oracle, n, 7, len(lens), 0, X=X, y=y, qid=qid)
+    base = rng.integers(-4, 5, size=(3, 7)) / 4.0
+    fids = [0, 3, 6]
+    cands = [[0.0, 0.5, -1.0, 2.0, 0.25]] * 3
+    try:
+        for name, metric, depth in [("ndcg@10", 0, 10), ("ndcg", 0, -1), ("map", 1, -1), ("rr", 2, -1)]:
+            plan = dev.plan(metric, depth)
+            _check(oracle, ods, X, plan, name, base, fids, cands, exact=True)
+    finally:
+        dev.close()
+    # one document more than the kernel ranks per query: the entry point must refuse, loudly
+    qid2 = np.concatenate([qid, np.full(257, 999)]).astype(np.int64)
+    X2 = np.concatenate([X, rng.normal(size=(257, 7)).astype(np.float32)])
+    y2 = np.concatenate([y, rng.integers(0, 3, 257).astype(np.float64)])
+    qidx, nq = dense_qidx(qid2)
+    dev2 = DevDataset(X2, y2.astype(np.float32), qidx, nq)
+    try:
+        plan = dev2.plan(0, 10)
+        assert dev2.lib.fr_dev_plan_has_fast_sweep(plan.ptr) == 0
+        with pytest.raises(RuntimeError, match="not available"):
+            plan.coord_sweeps(base, fids, cands, fast=True)
+        plan.coord_sweeps(base, fids, cands)  # the exact kernel still serves it
+    finally:
+        dev2.close()
+
+
+def test_negative_fractional_and_many_distinct_gains(oracle):
+    rng = np.random.default_rng(13)
+    n, d, q = 3000, 6, 80
+    qid = np.sort(rng.integers(0, q, n)).astype(np.int64)
+    X = rng.integers(0, 5, size=(n, d)).astype(np.float32)
+    base = rng.integers(-4, 5, size=(2, d)) / 4.0
+    cands = [[0.0, 1.0, -0.5], [0.25, 2.0, -2.0]]
+    # (a) negative and fractional gains: documents below AND above the zero-gain block contribute
+    y = rng.choice([-1.0, -0.5, 0.0, 0.0, 0.5, 1.0, 2.5], size=n)
+    _, _, _, ods, dev = _mk(oracle, n, d, q, 0, X=X, y=y, qid=qid)
+    try:
+        for name, metric, depth in [("ndcg@10", 0, 10), ("ndcg", 0, -1), ("map", 1, -1), ("rr", 2, -1)]:
+            sums, pq = dev.plan(metric, depth).coord_sweeps(base, [1, 4], cands, fast=True, per_query=True)
+            for r, f in enumerate([1, 4]):
+                for k, wv in enumerate(cands[r]):
+                    w = base[r].copy()
+                    w[f] = wv
+                    try:
+                        exp = oracle.evaluate_scores(ods, oracle.score_linear(X, w), name)
+                    except Exception:
+                        continue
+                    assert np.array_equal(pq[r, k], exp), (name, r, k)
+    finally:
+        dev.close()
+    # (b) more than 255 distinct gain values: no discount table, terms are divided on the device
+    y = np.round(rng.random(n) * 3.0, 3) * (rng.random(n) < 0.5)
+    _, _, _, ods, dev = _mk(oracle, n, d, q, 0, X=X, y=y, qid=qid)
+    try:
+        assert len(np.unique(y.astype(np.float32))) > 255
+        plan = dev.plan(0, 10)
+        _check(oracle, ods, X, plan, "ndcg@10", base, [1, 4], cands, exact=True)
+    finally:
+        dev.close()
+
+
+def test_subsets_truncation_and_inert_coordinates(oracle):
+    X, y, qid, ods, dev = _mk(oracle, 3000, 10, 90, seed=11)
+    rng = np.random.default_rng(3)
+    names = ods.query_names
+    pick = [5, 17, 3, 60, 61, 62]
+    try:
+        # query subset + instance subset
+        keep, offs = [], [0]
+        for i in pick:
+            ids = ods.by_query[names[i]]
+            keep.extend(ids[::2])
+            offs.append(len(keep))
+        plan = dev.plan(0, 5, query_ids=pick, inst=(offs, keep))
+        ods.set_view([names[i] for i in pick], instances=keep)
+        base = rng.normal(size=(2, 10))
+        _check(oracle, ods, X, plan, "ndcg@5", base, [2, 9], [_line(base[0, 2], 7), _line(base[1, 9], 7)],
+               max_flip_frac=0.0)
+        ods.set_view(names)
+        # weight vector shorter than the row (zip truncation) and a coordinate beyond the row
+        plan = dev.plan(0, 10)
+        short = rng.normal(size=(2, 6))
+        _check(oracle, ods, X, plan, "ndcg@10", short, [1, 5], [_line(short[0, 1], 4), _line(short[1, 5], 4)],
+               max_flip_frac=0.0)
+        wide = rng.normal(size=(1, 13))
+        sums, pq = plan.coord_sweeps(wide, [12], [[0.0, 1.0, -3.0]], fast=True, per_query=True)
+        exp = oracle.evaluate_scores(ods, oracle.score_linear(X, wide[0]), "ndcg@10")
+        for k in range(3):
+            assert np.array_equal(pq[0, k], exp)
+        # a sweep without candidates next to one with
+        sums = plan.coord_sweeps(short, [1, 5], [[], [0.5]], fast=True)
+        w = short[1].copy()
+        w[5] = 0.5
+        assert int(sums[1, 0]) == fx_sum(oracle.evaluate_scores(ods, oracle.score_linear(X, w), "ndcg@10"))
+    finally:
+        ods.set_view(names)
+        dev.close()
+
+
+def test_fast_sweep_reports_nan(oracle):
+    X, y, qid, ods, dev = _mk(oracle, 300, 4, 10, seed=12)
+    try:
+        plan = dev.plan(0, 5)
+        with pytest.raises(RuntimeError, match="NaN"):
+            plan.coord_sweeps(np.array([[np.nan, 0.0, 0.0, 0.0]]), [1], [[0.0, 1.0]], fast=True)
+    finally:
+        dev.close()
