@@ -232,6 +232,11 @@ struct FastPlan {
     DevBuf<uint2> tasks;             // .x = qs | qe << 16, .y = t0 | n << 16 (tile-local documents)
     DevBuf<uint8_t> pd_cls;          // plan doc -> gain class
     DevBuf<double> disc_tbl;         // [n_cls][tbl_r]  (2^gain - 1) / log2(r + 2)
+    // per-call work buffers: the call's candidates flattened into rows
+    DevBuf<double> row_w;            // candidate weight of the row
+    DevBuf<uint32_t> row_meta;       // sweep of the row (index inside its group of 8 sweeps)
+    DevBuf<uint32_t> row_out;        // where the row's sum goes: sweep * cand_stride + candidate
+    DevBuf<uint32_t> grp_row_off;    // rows of sweep group g: [grp_row_off[g], grp_row_off[g + 1])
 };
 
 struct FastView {
@@ -240,6 +245,7 @@ struct FastView {
     const uint8_t *pd_cls;
     const double *disc_tbl;
     uint32_t tbl_r;
+    uint32_t n_cls;
 };
 
 struct fr_dev_plan {

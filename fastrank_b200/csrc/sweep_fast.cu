@@ -30,18 +30,24 @@
 namespace {
 
 constexpr int kMaxSweeps = 8;  // sweeps sharing one pass over X (one blockIdx.y group)
+constexpr int kMaxRows = kMaxSweeps * 32;
+constexpr int kSmemTbl = 256;  // discount-table entries kept in shared memory
 constexpr double kFx = 1099511627776.0;
 static_assert(FR_FX_BITS == 40, "kFx must match FR_FX_BITS");
 
+// The candidates of a call are flattened into ROWS, sorted by sweep; a warp ranks 32 rows at a
+// time (lane = row), so lanes are filled across sweep boundaries (8 x 26 candidates = 7 groups
+// of 32 instead of 8 of 26).
 struct FastArgs {
-    const double *base_w;    // [n_sweeps][wlen]
-    const uint32_t *fid;     // [n_sweeps]
-    const double *cand_w;    // [n_sweeps][cand_stride]
-    const uint32_t *n_cand;  // [n_sweeps]
-    long long *sums;         // [n_sweeps][cand_stride]
-    double *perq;            // nullptr or [n_sweeps][cand_stride][nq_view]
-    uint32_t n_sweeps, wlen, cand_stride, cand_off;
-    uint32_t kp;  // candidates per pass (score rows, slot row stride), <= 32
+    const double *base_wt;        // [n_groups][dm][kMaxSweeps] base weights, transposed per group, dm rounded up to 8
+    const uint32_t *fid;          // [n_sweeps]
+    const double *row_w;          // [n_rows]
+    const uint32_t *row_meta;     // [n_rows] sweep index inside the row's group of kMaxSweeps
+    const uint32_t *row_out;      // [n_rows] index into sums / perq
+    const uint32_t *grp_row_off;  // [n_groups + 1]
+    long long *sums;
+    double *perq;  // nullptr or [n_out][nq_view]
+    uint32_t n_sweeps, wlen;
     uint32_t dm;  // min(wlen, features): zip() truncation of dense_dataset.rs:67-76
     int *err;
 };
@@ -55,96 +61,104 @@ __device__ __forceinline__ void count_gt(unsigned &cnt, double a, double b) {
     asm("{ .reg .pred p; setp.gt.f64 p, %1, %2; @p add.u32 %0, %0, 1; }" : "+r"(cnt) : "d"(a), "d"(b));
 }
 
+// X is streamed once per launch: keep it out of L1 so the (re-used) weight table stays there.
+__device__ __forceinline__ float ld_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
+template <int TB>
+struct SlotType {
+    typedef uint8_t type;  // document ids 1..128 / gain classes 1..255
+};
+template <>
+struct SlotType<256> {
+    typedef uint16_t type;
+};
+
 struct SmemLayout {
-    size_t w, cand, score, gexp, sum, slot, tasks, cls, misc, total;
-    __host__ __device__ SmemLayout(int tb, uint32_t dm, uint32_t kp) {
+    size_t score, roww, sum, tbl, gexp, slot0, slot1, tasks, cls, rowsw, misc, total;
+    __host__ __device__ SmemLayout(int tb, int slot_bytes) {
         size_t o = 0;
-        w = o;      o += align16(sizeof(double) * (size_t)(dm ? dm : 1) * kMaxSweeps);
-        cand = o;   o += sizeof(double) * kMaxSweeps * 32;
-        score = o;  o += align16(sizeof(double) * (size_t)kp * (tb + 1));
+        score = o;  o += align16(sizeof(double) * 32 * (size_t)(tb + 1));
+        roww = o;   o += sizeof(double) * kMaxRows;
+        sum = o;    o += sizeof(unsigned long long) * kMaxRows;
+        tbl = o;    o += sizeof(double) * kSmemTbl;
         gexp = o;   o += sizeof(double) * tb;
-        sum = o;    o += sizeof(unsigned long long) * kMaxSweeps * 32;
-        slot = o;   o += align16(sizeof(uint16_t) * (size_t)tb * kp);
+        slot0 = o;  o += align16((size_t)slot_bytes * tb * 32);
+        slot1 = o;  o += align16((size_t)slot_bytes * tb * 32);
         tasks = o;  o += sizeof(uint2) * tb;
         cls = o;    o += align16(tb);
+        rowsw = o;  o += kMaxRows;
         misc = o;   o += 256;
         total = o;
     }
 };
 
 // misc words
-enum { M_F = 0, M_K = 8, M_SPEC = 16, M_NSPEC = 25, M_CTR = 26 };
+enum { M_F = 0, M_CTR = 18, M_SWROW = 20 /* 9 entries */ };
 
 template <int TB, int TD>
 __global__ void __launch_bounds__(TB, (TB == 128 ? 4 : 1))
 sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef typename SlotType<TB>::type slot_t;
     constexpr int NS = kMaxSweeps;
     constexpr int ROW = TB + 1;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t s0 = blockIdx.y * NS;
     const int ns = (int)min((uint32_t)NS, A.n_sweeps - s0);
-    const uint32_t dm = A.dm, KP = A.kp;
-    const SmemLayout L(TB, dm, KP);
-    double *s_w = (double *)(smem_raw + L.w);  // [dm][NS]
-    double *s_cand = (double *)(smem_raw + L.cand);
-    double *s_score = (double *)(smem_raw + L.score);  // [KP][ROW]
-    double *s_gexp = (double *)(smem_raw + L.gexp);
+    const uint32_t dm = A.dm;
+    const uint32_t row0 = A.grp_row_off[blockIdx.y];
+    const int R = (int)(A.grp_row_off[blockIdx.y + 1] - row0);  // rows of this sweep group
+    const int G = (R + 31) >> 5;
+    const SmemLayout L(TB, (int)sizeof(slot_t));
+    double *s_score = (double *)(smem_raw + L.score);  // [32][ROW]
+    double *s_roww = (double *)(smem_raw + L.roww);
     unsigned long long *s_sum = (unsigned long long *)(smem_raw + L.sum);
-    uint16_t *s_slot = (uint16_t *)(smem_raw + L.slot);  // [TB][KP]
+    double *s_tbl = (double *)(smem_raw + L.tbl);
+    double *s_gexp = (double *)(smem_raw + L.gexp);
+    slot_t *s_slot0 = (slot_t *)(smem_raw + L.slot0);
+    const size_t slot_stride = (L.slot1 - L.slot0) / sizeof(slot_t);
     uint2 *s_tasks = (uint2 *)(smem_raw + L.tasks);
     uint8_t *s_cls = (uint8_t *)(smem_raw + L.cls);
+    uint8_t *s_rowsw = (uint8_t *)(smem_raw + L.rowsw);
     int *s_misc = (int *)(smem_raw + L.misc);
+    const bool use_tbl = F.disc_tbl != nullptr;
+    const bool tbl_in_smem = use_tbl && F.n_cls * F.tbl_r <= (uint32_t)kSmemTbl;
+    const double *tbl = tbl_in_smem ? s_tbl : F.disc_tbl;
 
-    // ---- per-launch setup: weights, candidates, the coordinates that need special handling
-    for (uint32_t idx = t; idx < dm * NS; idx += TB) {
-        const uint32_t j = idx / NS, s = idx % NS;
-        s_w[idx] = (int)s < ns ? A.base_w[(size_t)(s0 + s) * A.wlen + j] : 0.0;
-    }
-    for (int idx = t; idx < NS * 32; idx += TB) {
-        const int s = idx >> 5, k = idx & 31;
-        double v = 0.0;
-        if (s < ns) {
-            const int K = (int)A.n_cand[s0 + s] - (int)A.cand_off;
-            if (k < K) v = A.cand_w[(size_t)(s0 + s) * A.cand_stride + A.cand_off + k];
-        }
-        s_cand[idx] = v;
+    // ---- per-launch setup ----
+    for (int idx = t; idx < kMaxRows; idx += TB) {
+        s_roww[idx] = idx < R ? A.row_w[row0 + idx] : 0.0;
+        s_rowsw[idx] = idx < R ? (uint8_t)A.row_meta[row0 + idx] : (uint8_t)0;
         s_sum[idx] = 0ull;
     }
+    if (tbl_in_smem)
+        for (uint32_t idx = t; idx < F.n_cls * F.tbl_r; idx += TB) s_tbl[idx] = F.disc_tbl[idx];
     if (t == 0) {
-        int nspec = 0;
-        for (int s = 0; s < NS; ++s) {
-            int K = 0;
-            uint32_t f = 0xffffffffu;
-            if (s < ns) {
-                K = (int)A.n_cand[s0 + s] - (int)A.cand_off;
-                K = K < 0 ? 0 : (K > (int)KP ? (int)KP : K);
-                f = A.fid[s0 + s];
-            }
-            s_misc[M_K + s] = K;
-            s_misc[M_F + s] = (int)f;
-            if (K > 0 && f < dm) {  // insert into the sorted, de-duplicated list
-                int p = 0;
-                while (p < nspec && (uint32_t)s_misc[M_SPEC + p] < f) ++p;
-                if (p == nspec || (uint32_t)s_misc[M_SPEC + p] != f) {
-                    for (int u = nspec; u > p; --u) s_misc[M_SPEC + u] = s_misc[M_SPEC + u - 1];
-                    s_misc[M_SPEC + p] = (int)f;
-                    ++nspec;
-                }
-            }
+        // first row of every sweep (rows are sorted by sweep), and the coordinates that split a sum
+        int r = 0;
+        for (int s = 0; s <= NS; ++s) {
+            while (r < R && (int)A.row_meta[row0 + r] < s) ++r;
+            s_misc[M_SWROW + s] = r;
         }
-        s_misc[M_NSPEC] = nspec;
+        for (int s = 0; s < NS; ++s) {
+            const bool has_rows = s_misc[M_SWROW + s + 1] > s_misc[M_SWROW + s];
+            s_misc[M_F + s] = (s < ns && has_rows) ? (int)A.fid[s0 + s] : -1;
+        }
     }
     __syncthreads();
     uint32_t fs[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) fs[s] = (uint32_t)s_misc[M_F + s];
-    const int nspec = s_misc[M_NSPEC];
     int nan_seen = 0;
-    const int kk = lane < (int)KP ? lane : (int)KP - 1;  // score row this lane reads
-    const double *myrow = s_score + (size_t)kk * ROW;
+    const double *myrow = s_score + (size_t)lane * ROW;
+    const uint32_t dm8 = (dm + 7) & ~7u;
+    const double *__restrict__ wg = A.base_wt + (size_t)blockIdx.y * dm8 * NS;
 
     for (uint32_t tile = blockIdx.x; tile < P.nt; tile += gridDim.x) {
         const uint32_t doc0 = P.tile_doc_off[tile];
@@ -153,90 +167,91 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
         const uint32_t pos = active ? P.pd_pos[doc0 + t] : 0u;
         const uint32_t task0 = F.tile_task_off[tile];
         const int ntask = (int)(F.tile_task_off[tile + 1] - task0);
+        const uint32_t q0 = P.tile_q_off[tile];
+        const int nqt = (int)(P.tile_q_off[tile + 1] - q0);
         if (t < ntask) s_tasks[t] = F.tasks[task0 + t];
-        s_gexp[t] = active ? __ldg(P.gexp + pos) : 0.0;
+        if (!use_tbl) s_gexp[t] = active ? __ldg(P.gexp + pos) : 0.0;
         s_cls[t] = active ? __ldg(F.pd_cls + doc0 + t) : (uint8_t)0;
 
         // ---- phase 1: one pass over the tile's features for every sweep ----
-        double acc[NS], pre[NS], xf[NS];
+        // acc[s] = sum_j x_j * w_sj, j ascending, separate multiply and add; the host zeroed
+        // w at the coordinate the sweep varies, whose feature value is fetched on its own.
+        double acc[NS];
+        float xf[NS];
+        {
+            const float *__restrict__ xp = P.x + pos;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) acc[s] = pre[s] = xf[s] = 0.0;
-        const float *__restrict__ xp = P.x + pos;
-        uint32_t j = 0;
-        for (int si = 0; si <= nspec; ++si) {
-            const uint32_t sp = si < nspec ? (uint32_t)s_misc[M_SPEC + si] : dm;
-            for (; j + 8 <= sp; j += 8) {
-                float xv[8];
+            for (int s = 0; s < NS; ++s) {
+                acc[s] = 0.0;
+                xf[s] = fs[s] < dm ? ld_stream(xp + (size_t)fs[s] * P.ld) : 0.f;
+            }
+            float cur[8], nxt[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) xv[u] = __ldg(xp + (size_t)(j + u) * P.ld);
+            for (int u = 0; u < 8; ++u) cur[u] = (uint32_t)u < dm ? ld_stream(xp + (size_t)u * P.ld) : 0.f;
+            // the weight table is zero-padded to a multiple of 8 coordinates: no guards on the math
+            for (uint32_t j0 = 0; j0 < dm; j0 += 8) {
+                if (j0 + 16 <= dm) {  // prefetch the next block while this one is consumed
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) nxt[u] = ld_stream(xp + (size_t)(j0 + 8 + u) * P.ld);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        nxt[u] = j0 + 8 + u < dm ? ld_stream(xp + (size_t)(j0 + 8 + u) * P.ld) : 0.f;
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const double xd = (double)xv[u];
-                    const double *wj = s_w + (size_t)(j + u) * NS;
+                    const double xd = (double)cur[u];
+                    const double2 *__restrict__ wj = (const double2 *)(wg + (size_t)(j0 + u) * NS);
 #pragma unroll
-                    for (int s = 0; s < NS; ++s) acc[s] = __dadd_rn(acc[s], __dmul_rn(xd, wj[s]));
-                }
-            }
-            for (; j < sp; ++j) {
-                const double xd = (double)__ldg(xp + (size_t)j * P.ld);
-                const double *wj = s_w + (size_t)j * NS;
-#pragma unroll
-                for (int s = 0; s < NS; ++s) acc[s] = __dadd_rn(acc[s], __dmul_rn(xd, wj[s]));
-            }
-            if (sp < dm) {  // a coordinate some sweep varies: split that sweep's sum here
-                const double xd = (double)__ldg(xp + (size_t)sp * P.ld);
-                const double *wj = s_w + (size_t)sp * NS;
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    if (fs[s] == sp) {
-                        pre[s] = acc[s];
-                        xf[s] = xd;
-                        acc[s] = 0.0;
-                    } else {
-                        acc[s] = __dadd_rn(acc[s], __dmul_rn(xd, wj[s]));
+                    for (int s = 0; s < NS; s += 2) {
+                        const double2 w2 = __ldg(wj + (s >> 1));
+                        acc[s] = __dadd_rn(acc[s], __dmul_rn(xd, w2.x));
+                        acc[s + 1] = __dadd_rn(acc[s + 1], __dmul_rn(xd, w2.y));
                     }
                 }
-                j = sp + 1;
-            }
-        }
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            if (fs[s] >= dm) {  // the varied coordinate lies beyond the row: candidates are inert
-                pre[s] = acc[s];
-                acc[s] = 0.0;
-                xf[s] = 0.0;
+                for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
             }
         }
 
-        // ---- phase 2: per sweep, score the candidates, rank, fold the metric ----
-        for (int s = 0; s < ns; ++s) {
-            const int K = s_misc[M_K + s];
-            if (K == 0) continue;
-            double ps = pre[0], xs = xf[0], ss = acc[0];
+        // scores of row group g -> s_score, and clear the slot buffer the group will use
+        auto score_group = [&](int g) {
+            const int rbeg = g << 5, rend = min(R, rbeg + 32);
+            double *col = s_score + t;
+            int r = rbeg;
+            while (r < rend) {
+                const int s = s_rowsw[r];
+                const int seg_end = min(rend, s_misc[M_SWROW + s + 1]);
+                double ss = acc[0];
+                float xs32 = xf[0];
 #pragma unroll
-            for (int u = 1; u < NS; ++u) {
-                if (s == u) {
-                    ps = pre[u];
-                    xs = xf[u];
-                    ss = acc[u];
+                for (int u = 1; u < NS; ++u) {
+                    if (s == u) {
+                        ss = acc[u];
+                        xs32 = xf[u];
+                    }
                 }
-            }
-            {
-                const double *cw = s_cand + s * 32;
-                double *col = s_score + t;
+                const double xs = (double)xs32;
 #pragma unroll 4
-                for (int k = 0; k < K; ++k) {
-                    const double sc = __dadd_rn(__dadd_rn(ps, __dmul_rn(xs, cw[k])), ss);
+                for (; r < seg_end; ++r) {
+                    const double sc = __dadd_rn(ss, __dmul_rn(xs, s_roww[r]));
                     if (sc != sc) nan_seen |= active ? 1 : 0;
-                    col[(size_t)k * ROW] = sc;
+                    col[(size_t)(r - rbeg) * ROW] = sc;
                 }
-                uint4 *z = (uint4 *)s_slot;
-                const int nz = (int)(((size_t)TB * KP * sizeof(uint16_t)) / sizeof(uint4));
-                for (int i = t; i < nz; i += TB) z[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (t == 0) s_misc[M_CTR] = 0;
             }
-            __syncthreads();
-            // -- rank by counting; lane = candidate, TD documents per task --
+            uint4 *z = (uint4 *)(s_slot0 + (size_t)(g & 1) * slot_stride);
+            constexpr int nz = (int)((sizeof(slot_t) * TB * 32) / sizeof(uint4));
+#pragma unroll
+            for (int i = t; i < nz; i += TB) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (t == 0) s_misc[M_CTR] = 0;
+        };
+
+        if (G > 0) score_group(0);
+        __syncthreads();
+        for (int g = 0; g < G; ++g) {
+            slot_t *slots = s_slot0 + (size_t)(g & 1) * slot_stride;
+            const int nrow = min(32, R - (g << 5));  // live lanes of this group
+            // -- rank by counting; lane = row, TD documents per task --
             {
                 int ti = 0;
                 if (lane == 0) ti = atomicAdd(&s_misc[M_CTR], 1);
@@ -280,109 +295,107 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
 #pragma unroll
                         for (int i = 0; i < TD; ++i) count_gt(cnt[i], sj, st[i]);
                     }
-                    if (lane < K) {
+                    if (lane < nrow) {
                         const unsigned len = (unsigned)(qe - qs);
                         const unsigned lim =
                             (P.metric == FR_METRIC_NDCG && (unsigned)P.depth < len) ? (unsigned)P.depth : len;
 #pragma unroll
-                        for (int i = 0; i < TD; ++i)
-                            if (i < n && cnt[i] < lim)
-                                s_slot[(size_t)(qs + cnt[i]) * KP + lane] = (uint16_t)(t0 + i + 1);
+                        for (int i = 0; i < TD; ++i) {
+                            if (i < n && cnt[i] < lim) {
+                                // what the fold needs: the gain class (table), else the document
+                                const unsigned tag = (P.metric == FR_METRIC_NDCG && use_tbl)
+                                                         ? (unsigned)s_cls[t0 + i] + 1u
+                                                         : (unsigned)(t0 + i + 1);
+                                slots[(size_t)(qs + cnt[i]) * 32 + lane] = (slot_t)tag;
+                            }
+                        }
                     }
                     ti = __shfl_sync(0xffffffffu, tnext, 0);
                 }
             }
             __syncthreads();
-            // -- one warp per query folds the slots in rank order --
-            {
-                const uint32_t q0 = P.tile_q_off[tile];
-                const int nqt = (int)(P.tile_q_off[tile + 1] - q0);
-                for (int ql = warp; ql < nqt; ql += TB / 32) {
-                    const uint32_t pq = q0 + ql;
-                    const uint32_t loc = P.pq_local[pq];
-                    const uint32_t start = loc & 0xffffu, len = loc >> 16;
-                    const double norm = P.pq_norm[pq];
-                    const uint16_t *sl = s_slot + (size_t)start * KP + kk;
-                    double value = 0.0;
-                    if (P.metric == FR_METRIC_NDCG) {
-                        if (norm == norm) {  // Some(ideal), evaluators.rs:351-358
-                            const uint32_t lim = len < (uint32_t)P.depth ? len : (uint32_t)P.depth;
-                            double dcg = 0.0;
-                            for (uint32_t r0 = 0; r0 < lim; r0 += 8) {
-                                double term[8];
+            // -- one warp per query folds the slots in rank order; then the next group's scores --
+            for (int ql = warp; ql < nqt; ql += TB / 32) {
+                const uint32_t pq = q0 + ql;
+                const uint32_t loc = P.pq_local[pq];
+                const uint32_t start = loc & 0xffffu, len = loc >> 16;
+                const double norm = P.pq_norm[pq];
+                const slot_t *sl = slots + (size_t)start * 32 + lane;
+                double value = 0.0;
+                if (P.metric == FR_METRIC_NDCG) {
+                    if (norm == norm) {  // Some(ideal), evaluators.rs:351-358
+                        const uint32_t lim = len < (uint32_t)P.depth ? len : (uint32_t)P.depth;
+                        double dcg = 0.0;
+                        for (uint32_t r0 = 0; r0 < lim; r0 += 8) {
+                            unsigned id[8];
+                            double term[8];
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) {
-                                    term[u] = 0.0;
+                            for (int u = 0; u < 8; ++u) id[u] = r0 + u < lim ? sl[(size_t)(r0 + u) * 32] : 0u;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                term[u] = 0.0;
+                                if (id[u]) {
                                     const uint32_t r = r0 + u;
-                                    if (r < lim) {
-                                        const unsigned id = sl[(size_t)r * KP];
-                                        if (id) {
-                                            if (F.disc_tbl)
-                                                term[u] = __ldg(F.disc_tbl + (size_t)s_cls[id - 1] * F.tbl_r + r);
-                                            else
-                                                term[u] = s_gexp[id - 1] / __ldg(P.lg2 + r);
-                                        }
-                                    }
+                                    if (use_tbl)
+                                        term[u] = tbl[(size_t)(id[u] - 1) * F.tbl_r + r];
+                                    else
+                                        term[u] = s_gexp[id[u] - 1] / __ldg(P.lg2 + r);
                                 }
+                            }
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) dcg = __dadd_rn(dcg, term[u]);
-                            }
-                            if (dcg > norm) atomicOr(A.err, ERR_DCG_ABOVE_IDEAL);
-                            value = dcg / norm;
+                            for (int u = 0; u < 8; ++u) dcg = __dadd_rn(dcg, term[u]);
                         }
-                    } else if (P.metric == FR_METRIC_AP) {
-                        if (norm > 0.0) {
-                            unsigned recall = 0;
-                            double sum = 0.0;
-                            for (uint32_t r = 0; r < len; ++r) {
-                                if (sl[(size_t)r * KP]) {
-                                    recall += 1;
-                                    sum = __dadd_rn(sum, (double)recall / (double)(r + 1));
-                                }
-                            }
-                            value = sum / norm;
-                        }
-                    } else {
-                        for (uint32_t r = 0; r < len; ++r) {
-                            if (sl[(size_t)r * KP]) {
-                                value = 1.0 / (double)(r + 1);
-                                break;
-                            }
-                        }
+                        if (dcg > norm) atomicOr(A.err, ERR_DCG_ABOVE_IDEAL);
+                        value = dcg / norm;
                     }
-                    if (lane < K) {
-                        if (A.perq)
-                            A.perq[((size_t)(s0 + s) * A.cand_stride + A.cand_off + lane) * P.nq_view +
-                                   P.pq_view[pq]] = value;
-                        const long long fx = __double2ll_rn(value * kFx);
-                        atomicAdd(&s_sum[s * 32 + lane], (unsigned long long)fx);
+                } else if (P.metric == FR_METRIC_AP) {
+                    if (norm > 0.0) {
+                        unsigned recall = 0;
+                        double sum = 0.0;
+                        for (uint32_t r = 0; r < len; ++r) {
+                            if (sl[(size_t)r * 32]) {
+                                recall += 1;
+                                sum = __dadd_rn(sum, (double)recall / (double)(r + 1));
+                            }
+                        }
+                        value = sum / norm;
+                    }
+                } else {
+                    for (uint32_t r = 0; r < len; ++r) {
+                        if (sl[(size_t)r * 32]) {
+                            value = 1.0 / (double)(r + 1);
+                            break;
+                        }
                     }
                 }
+                if (lane < nrow) {
+                    const int row = (g << 5) + lane;
+                    if (A.perq)
+                        A.perq[(size_t)A.row_out[row0 + row] * P.nq_view + P.pq_view[pq]] = value;
+                    const long long fx = __double2ll_rn(value * kFx);
+                    atomicAdd(&s_sum[row], (unsigned long long)fx);
+                }
             }
+            if (g + 1 < G) score_group(g + 1);
             __syncthreads();
         }
     }
     if (nan_seen) atomicOr(A.err, ERR_NAN_SCORE);
     __syncthreads();
-    for (int idx = t; idx < ns * 32; idx += TB) {
-        const int s = idx >> 5, k = idx & 31;
-        if (k < s_misc[M_K + s])
-            atomicAdd((unsigned long long *)(A.sums + (size_t)(s0 + s) * A.cand_stride + A.cand_off + k),
-                      s_sum[idx]);
-    }
+    for (int idx = t; idx < R; idx += TB)
+        atomicAdd((unsigned long long *)(A.sums + A.row_out[row0 + idx]), s_sum[idx]);
 }
 
 template <int TB, int TD>
-int launch_fast(fr_dev_plan *pl, const FastArgs &a, cudaStream_t stream) {
-    const SmemLayout L(TB, a.dm, a.kp);
+int launch_fast(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStream_t stream) {
+    const SmemLayout L(TB, (int)sizeof(typename SlotType<TB>::type));
     auto kernel = sweep_fast_kernel<TB, TD>;
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TB, L.total));
     if (occ < 1) return fail("sweep_fast_kernel does not fit on an SM");
-    const uint32_t gy = (a.n_sweeps + kMaxSweeps - 1) / kMaxSweeps;
     uint64_t total = (uint64_t)pl->sm_count * (uint64_t)occ;
-    uint32_t gx = (uint32_t)std::max<uint64_t>(1, total / gy);
+    uint32_t gx = (uint32_t)std::max<uint64_t>(1, total / n_groups);
     if (gx > pl->nt) gx = pl->nt;
     PlanView pv = pl->view();
     FastView fv;
@@ -391,9 +404,10 @@ int launch_fast(fr_dev_plan *pl, const FastArgs &a, cudaStream_t stream) {
     fv.pd_cls = pl->fast.pd_cls.p;
     fv.disc_tbl = pl->fast.n_cls ? pl->fast.disc_tbl.p : nullptr;
     fv.tbl_r = pl->fast.tbl_r;
+    fv.n_cls = pl->fast.n_cls;
     auto *ev = pl->ds->prof_slot();
     if (ev) cudaEventRecord(ev->first, stream);
-    kernel<<<dim3(gx, gy), TB, L.total, stream>>>(pv, fv, a);
+    kernel<<<dim3(gx, n_groups), TB, L.total, stream>>>(pv, fv, a);
     if (ev) cudaEventRecord(ev->second, stream);
     LAUNCHED();
     CU(cudaGetLastError());
@@ -508,50 +522,93 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         return fail("fr_dev_eval_coord_sweeps_fast: not available for this plan (" + pl->fast.why + ")");
     if (n_sweeps == 0) return 0;
     fr_dev_dataset *ds = pl->ds;
+    FastPlan &fp = pl->fast;
     CU(cudaSetDevice(ds->device));
     cudaStream_t s = ds->stream;
-    uint32_t kmax = 0;
-    for (size_t r = 0; r < n_sweeps; ++r) {
-        if (n_cand[r] > cand_stride) return fail("fr_dev_eval_coord_sweeps_fast: n_cand > cand_stride");
-        kmax = std::max(kmax, n_cand[r]);
-    }
     const size_t total = n_sweeps * cand_stride;
-    CU(pl->w_dev.ensure(n_sweeps * wlen));
-    CU(pl->cand_dev.ensure(total));
+    // flatten the candidates into rows, sorted by sweep; a sweep group holds at most
+    // kMaxSweeps sweeps and kMaxRows rows, so a group with more candidates is served in passes
+    std::vector<uint32_t> cursor(n_sweeps, 0);
+    for (size_t r = 0; r < n_sweeps; ++r)
+        if (n_cand[r] > cand_stride) return fail("fr_dev_eval_coord_sweeps_fast: n_cand > cand_stride");
+    const uint32_t n_groups = (uint32_t)((n_sweeps + kMaxSweeps - 1) / kMaxSweeps);
     CU(pl->fid_dev.ensure(n_sweeps));
-    CU(pl->ncand_dev.ensure(n_sweeps));
     CU(pl->sums_dev.ensure(total));
     CU(pl->sums_host.ensure(total));
     if (out_per_query) CU(pl->perq_dev.ensure(total * (size_t)pl->nq_view));
-    CU(cudaMemcpyAsync(pl->w_dev.p, base_w, sizeof(double) * n_sweeps * wlen, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(pl->cand_dev.p, cand_w, sizeof(double) * total, cudaMemcpyHostToDevice, s));
+    {
+        // base weights transposed per sweep group: wt[g][j][s]; unused sweep columns are zero
+        const size_t dm = std::min<size_t>(wlen, ds->d);
+        const size_t dm8 = (dm + 7) & ~(size_t)7;
+        std::vector<double> wt((size_t)n_groups * std::max<size_t>(dm8, 8) * kMaxSweeps, 0.0);
+        for (size_t sw = 0; sw < n_sweeps; ++sw)
+            for (size_t j = 0; j < dm; ++j)
+                wt[((sw / kMaxSweeps) * dm8 + j) * kMaxSweeps + sw % kMaxSweeps] =
+                    j == fid[sw] ? 0.0 : base_w[sw * wlen + j];
+        CU(pl->w_dev.ensure(wt.size()));
+        CU(cudaMemcpyAsync(pl->w_dev.p, wt.data(), sizeof(double) * wt.size(), cudaMemcpyHostToDevice, s));
+    }
     CU(cudaMemcpyAsync(pl->fid_dev.p, fid, sizeof(uint32_t) * n_sweeps, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(pl->ncand_dev.p, n_cand, sizeof(uint32_t) * n_sweeps, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(pl->sums_dev.p, 0, sizeof(long long) * total, s));
     CU(cudaMemsetAsync(pl->err_dev.p, 0, sizeof(int), s));
     if (out_per_query)
         CU(cudaMemsetAsync(pl->perq_dev.p, 0, sizeof(double) * total * (size_t)pl->nq_view, s));
-    for (uint32_t c0 = 0; c0 < kmax; c0 += 32) {
+    std::vector<double> row_w;
+    std::vector<uint32_t> row_meta, row_out, grp_off;
+    for (;;) {
+        row_w.clear();
+        row_meta.clear();
+        row_out.clear();
+        grp_off.assign(1, 0);
+        bool any = false;
+        for (uint32_t g = 0; g < n_groups; ++g) {
+            const size_t sw0 = (size_t)g * kMaxSweeps, sw1 = std::min(n_sweeps, sw0 + kMaxSweeps);
+            uint32_t room = kMaxRows;
+            for (size_t sw = sw0; sw < sw1 && room > 0; ++sw) {
+                while (cursor[sw] < n_cand[sw] && room > 0) {
+                    row_w.push_back(cand_w[sw * cand_stride + cursor[sw]]);
+                    row_meta.push_back((uint32_t)(sw - sw0));
+                    row_out.push_back((uint32_t)(sw * cand_stride + cursor[sw]));
+                    ++cursor[sw];
+                    --room;
+                    any = true;
+                }
+            }
+            grp_off.push_back((uint32_t)row_w.size());
+        }
+        if (!any) break;
+        // (copies from pageable memory are staged before cudaMemcpyAsync returns, and the device
+        // buffers are overwritten in stream order behind the previous pass)
+        CU(fp.row_w.ensure(row_w.size()));
+        CU(fp.row_meta.ensure(row_meta.size()));
+        CU(fp.row_out.ensure(row_out.size()));
+        CU(fp.grp_row_off.ensure(grp_off.size()));
+        CU(cudaMemcpyAsync(fp.row_w.p, row_w.data(), sizeof(double) * row_w.size(), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(fp.row_meta.p, row_meta.data(), sizeof(uint32_t) * row_meta.size(),
+                           cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(fp.row_out.p, row_out.data(), sizeof(uint32_t) * row_out.size(),
+                           cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(fp.grp_row_off.p, grp_off.data(), sizeof(uint32_t) * grp_off.size(),
+                           cudaMemcpyHostToDevice, s));
         FastArgs a;
-        a.base_w = pl->w_dev.p;
+        a.base_wt = pl->w_dev.p;
         a.fid = pl->fid_dev.p;
-        a.cand_w = pl->cand_dev.p;
-        a.n_cand = pl->ncand_dev.p;
+        a.row_w = fp.row_w.p;
+        a.row_meta = fp.row_meta.p;
+        a.row_out = fp.row_out.p;
+        a.grp_row_off = fp.grp_row_off.p;
         a.sums = pl->sums_dev.p;
         a.perq = out_per_query ? pl->perq_dev.p : nullptr;
         a.n_sweeps = (uint32_t)n_sweeps;
         a.wlen = (uint32_t)wlen;
-        a.cand_stride = (uint32_t)cand_stride;
-        a.cand_off = c0;
-        a.kp = std::min<uint32_t>(32, kmax - c0);
         a.dm = (uint32_t)std::min<size_t>(wlen, ds->d);
         a.err = pl->err_dev.p;
         if (pl->nt == 0) continue;
         int rc;
         if (pl->tb == 128)
-            rc = pl->fast.td == 8 ? launch_fast<128, 8>(pl, a, s) : launch_fast<128, 4>(pl, a, s);
+            rc = fp.td == 8 ? launch_fast<128, 8>(pl, a, n_groups, s) : launch_fast<128, 4>(pl, a, n_groups, s);
         else
-            rc = pl->fast.td == 8 ? launch_fast<256, 8>(pl, a, s) : launch_fast<256, 4>(pl, a, s);
+            rc = fp.td == 8 ? launch_fast<256, 8>(pl, a, n_groups, s) : launch_fast<256, 4>(pl, a, n_groups, s);
         if (rc) return 1;
     }
     if (allreduce_sums(pl, pl->sums_dev.p, total, s)) return 1;
