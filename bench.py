@@ -110,7 +110,7 @@ class ClockSampler:
             os.makedirs(os.path.dirname(self.path), exist_ok=True)
             self.fp = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=self.fp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -279,7 +279,6 @@ def run_ours(args, rank, world, local_rank):
     ms = dev.timer_stop()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
-    clocks = sampler.stop()
     n_kern, kern_ms = dev.profile_read(reset=True)
     dev.profile(False)
     launches = int(lib.fr_dev_kernel_launches()) - launches0
@@ -344,6 +343,7 @@ def run_ours(args, rank, world, local_rank):
            "global_steps": stats["global_steps"], "final_train_ndcg10": final,
            "what": "from_numpy + train_model(CA, 8 restarts, seed 42, to convergence) + evaluate through the C ABI"}
     del ds, model
+    clocks = sampler.stop()  # sampled across both timed regions (device-timed steps and e2e)
 
     # ---- CPU baseline on the host cores (rank 0, single-GPU run only) -----------------------
     cpu = None
@@ -376,7 +376,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
