@@ -5,26 +5,31 @@
 //   score every document (dense_dataset.rs:67-76), sort each query by (score desc, gain asc,
 //   id asc) (evaluators.rs:33-49), NDCG / AP / RR per query, mean.
 //
-// Shape of the kernel (one CTA = one tile of whole queries, <= TB documents):
-//   phase 1  stream the tile's slice of X once (feature-major, coalesced): per document and
-//            per sweep s, with f = the coordinate the sweep varies,
-//                P = sum_{j<f} x_j w_j     xf = x_f     S = sum_{j>f} x_j w_j
-//            all in f64 with separate multiply and add, j ascending -- P is bit-identical to the
-//            reference's running sum when it reaches coordinate f.
-//   phase 2  per sweep: score[k][t] = (P + xf * cand_k) + S for the <= 32 candidates k (lane =
-//            candidate), then rank by counting: a warp task owns TD documents of one query that
-//            can contribute to the metric (gain != 0 for NDCG, gain > 0 for AP / RR) and walks
-//            the query once; documents before t count when score >= , documents after t when
-//            score > -- the reference's tie-break, because tile order is (gain asc, id asc).
-//            rank -> slot[rank] = document; one warp per query then folds the slots in rank
-//            order (the reference's left-to-right f64 sums) and accumulates round(value * 2^40).
+// Shape of the kernel (one CTA = one tile of whole queries, <= TB documents; persistent CTAs):
+//   phase 1  stream the tile's slice of X once (feature-major, coalesced, software-prefetched,
+//            kept out of L1): per document and per sweep s, with f_s = the coordinate the sweep
+//            varies,   T_s = sum_{j != f_s} x_j w_sj   (f64, separate multiply and add, j
+//            ascending; the host zeroes w at f_s)   and   xf_s = x_{f_s}.
+//   phase 2  the call's candidates are flattened into rows sorted by sweep; 32 rows at a time
+//            (lane = row, so lanes are filled across sweep boundaries):
+//              score[row][t] = T_s + xf_s * cand_row        (one f64 multiply, one add)
+//            then rank by counting: a warp task owns TD documents of one query that can
+//            contribute to the metric (gain != 0 for NDCG, gain > 0 for AP / RR) and walks the
+//            query once; documents before t count when score >=, documents after t when score >
+//            -- the reference's tie-break, because tile order is (gain asc, id asc).  One DSETP
+//            (FP64 pipe) + one predicated add (integer pipe) per comparison.
+//            rank -> slot[rank] = gain class; one warp per query then folds the slots in rank
+//            order (the reference's left-to-right f64 sums over a host-built table of
+//            (2^gain - 1) / log2(rank + 2)) and accumulates round(value * 2^40).
 //
-// Arithmetic contract ("fast" mode): candidate scores differ from the reference's left-to-right
-// dot product only in that the suffix S is summed before it is added (one rounding apart, ~1e-16
-// relative).  Whenever the induced ranking of a query is the same -- always, except for
+// Arithmetic contract ("fast" mode): a candidate's score is the reference's dot product with
+// the varied coordinate's term added last instead of in position -- a few roundings apart
+// (~1e-16 relative) from dense_dataset.rs:67-76.  Everything after the score is the
+// reference's: whenever the induced ranking of a query is the same -- always, except for
 // documents whose scores agree to the last bits -- the per-query metric is bit-identical to the
-// oracle, because terms and their summation order are the reference's.  The exact-order kernel
-// (device.cu coord_sweep_kernel) stays available behind fr_dev_eval_coord_sweeps.
+// oracle.  When the arithmetic is exact (e.g. dyadic weights on small-integer features, or an
+// all-zero base) the scores themselves are bit-identical, ties included.  The exact-order
+// kernel (device.cu coord_sweep_kernel) stays available behind fr_dev_eval_coord_sweeps.
 #include "device_common.cuh"
 
 namespace {

@@ -176,12 +176,13 @@ int fr_dev_eval_coord_sweeps(fr_dev_plan *plan, size_t n_sweeps, const double *b
                              size_t cand_stride, int64_t *out_sum_fx);
 
 /* The same line searches, batched: ONE pass over the feature matrix serves every sweep of the
- * call (groups of 8), candidates are scored as (prefix + x_f * cand) + suffix -- the reference's
- * running sum up to coordinate f, then one pre-summed suffix (one rounding away from the
- * reference's left-to-right order, ~1e-16 relative) -- and ranking, tie-break, metric terms and
- * their summation order are the reference's.  Per-query values are bit-identical to the exact
- * path whenever the ranking is.  This is what train_model uses (FASTRANK_SWEEP=exact selects
- * the entry point above instead).  out_per_query: NULL or n_sweeps x cand_stride x n_queries. */
+ * call (groups of 8 sweeps); a candidate's score is  T + x_f * cand  with T = the reference's
+ * left-to-right f64 sum over the other coordinates, i.e. the reference's dot product with the
+ * varied coordinate's term added last instead of in position (a few roundings, ~1e-16 relative,
+ * from dense_dataset.rs:67-76).  Ranking, tie-break, metric terms and their summation order are
+ * the reference's, so per-query values are bit-identical to the exact path whenever the ranking
+ * is.  This is what train_model uses (FASTRANK_SWEEP=exact selects the entry point above
+ * instead).  out_per_query: NULL or n_sweeps x cand_stride x n_queries (view order). */
 int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *plan, size_t n_sweeps, const double *base_w,
                                   size_t wlen, const uint32_t *fid, const double *cand_w,
                                   const uint32_t *n_cand, size_t cand_stride, int64_t *out_sum_fx,
