@@ -905,6 +905,7 @@ int fr_dev_model_create(fr_dev_dataset *ds, const uint64_t *code, size_t n_words
     m->n_words = n_words;
     CU(m->code.alloc(n_words));
     CU(cudaMemcpy(m->code.p, code, sizeof(uint64_t) * n_words, cudaMemcpyHostToDevice));
+    if (!getenv("FASTRANK_NO_FOREST_KERNEL") && build_forest(m.get(), code, n_words)) return 1;
     *out = m.release();
     return 0;
 }
@@ -920,12 +921,16 @@ int fr_dev_score_model(fr_dev_dataset *ds, const fr_dev_model *m, double *out_sc
     CU(cudaSetDevice(ds->device));
     cudaStream_t s = ds->stream;
     CU(ds->scores_inst.ensure(ds->n));
-    const int tb = 128;
-    model_score_kernel<<<(unsigned)((ds->n + tb - 1) / tb), tb, 0, s>>>(
-        ds->x.p, ds->ld, (uint32_t)ds->d, ds->n, m->code.p, ds->inst_of_pos_dev.p, nullptr,
-        ds->scores_inst.p);
-    LAUNCHED();
-    CU(cudaGetLastError());
+    if (m->forest.ok) {
+        if (launch_forest(ds, m, nullptr, ds->scores_inst.p, s)) return 1;
+    } else {
+        const int tb = 128;
+        model_score_kernel<<<(unsigned)((ds->n + tb - 1) / tb), tb, 0, s>>>(
+            ds->x.p, ds->ld, (uint32_t)ds->d, ds->n, m->code.p, ds->inst_of_pos_dev.p, nullptr,
+            ds->scores_inst.p);
+        LAUNCHED();
+        CU(cudaGetLastError());
+    }
     CU(cudaMemcpyAsync(out_scores, ds->scores_inst.p, sizeof(double) * ds->n, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return 0;
@@ -943,12 +948,16 @@ int fr_dev_eval_model(fr_dev_plan *pl, const fr_dev_model *m, int64_t *out_sum_f
     CU(cudaMemsetAsync(pl->sums_dev.p, 0, sizeof(long long), s));
     CU(cudaMemsetAsync(pl->err_dev.p, 0, sizeof(int), s));
     if (out_per_query) CU(pl->perq_dev.ensure(pl->nq_view));
-    const int tb = 128;
-    model_score_kernel<<<(unsigned)((ds->n + tb - 1) / tb), tb, 0, s>>>(
-        ds->x.p, ds->ld, (uint32_t)ds->d, ds->n, m->code.p, ds->inst_of_pos_dev.p, ds->scores_pos.p,
-        nullptr);
-    LAUNCHED();
-    CU(cudaGetLastError());
+    if (m->forest.ok) {
+        if (launch_forest(ds, m, ds->scores_pos.p, nullptr, s)) return 1;
+    } else {
+        const int tb = 128;
+        model_score_kernel<<<(unsigned)((ds->n + tb - 1) / tb), tb, 0, s>>>(
+            ds->x.p, ds->ld, (uint32_t)ds->d, ds->n, m->code.p, ds->inst_of_pos_dev.p, ds->scores_pos.p,
+            nullptr);
+        LAUNCHED();
+        CU(cudaGetLastError());
+    }
     if (pl->nt > 0 &&
         launch_scores_eval(pl, ds->scores_pos.p, pl->sums_dev.p, out_per_query ? pl->perq_dev.p : nullptr,
                            pl->err_dev.p, s))

@@ -191,10 +191,23 @@ struct fr_dev_dataset {
     }
 };
 
+// A model that is a forest of regression trees, flattened for trees.cu.
+struct Forest {
+    bool ok = false;
+    DevBuf<uint4> nodes;       // .x fid (FR_LEAF: leaf)  .y split (f32 bits)  .z/.w children, or leaf f64 lo/hi
+    DevBuf<uint32_t> roots;    // first node of every tree
+    DevBuf<double> weights;    // ensemble weights
+    DevBuf<uint2> hnodes;      // implicit-heap layout: [tree][2^levels - 1] {fid, split bits}
+    DevBuf<double> hleaves;    //                       [tree][2^levels]
+    uint32_t n_trees = 0, levels = 0, dstage = 1;
+    bool weighted = false, heap = false;
+};
+
 struct fr_dev_model {
     fr_dev_dataset *ds = nullptr;
     DevBuf<uint64_t> code;
     size_t n_words = 0;
+    Forest forest;
 };
 
 // Device-side view of a plan (passed to kernels by value).
@@ -298,6 +311,10 @@ namespace frbdev {
 // defined in device.cu
 int check_err_flags(int flags);
 int allreduce_sums(fr_dev_plan *pl, long long *dev, size_t count, cudaStream_t stream);
+// defined in trees.cu
+int build_forest(fr_dev_model *m, const uint64_t *code, size_t n_words);
+int launch_forest(fr_dev_dataset *ds, const fr_dev_model *m, double *out_pos, double *out_inst,
+                  cudaStream_t stream);
 // defined in sweep_fast.cu
 int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
                     const std::vector<uint32_t> &pq_local, const std::vector<uint32_t> &pq_doc0,

@@ -329,3 +329,49 @@ def test_random_forest_on_synthetic_dense(fr, oracle):
     exp = oracle.mean(oracle.evaluate_scores(ods, oracle.score_model(X, spec), "ndcg@10"))
     assert ds.evaluate_mean(model, "ndcg@10") == pytest.approx(exp, abs=1e-12)
     assert exp > 0.35  # random ranking on this generator gives ~0.26
+
+
+def test_forest_kernel_layouts_bit_exact(fr, oracle, monkeypatch):
+    """The three tree-scoring paths (implicit-heap forest kernel, pointer-layout forest kernel
+    for trees deeper than the heap limit, generic interpreter) against the oracle: single-leaf
+    trees, a 14-level chain, splits equal to feature values, features beyond the row, NaN-free
+    extremes."""
+    X, y, qid = synth(3000, 9, 70, seed=41)
+    X[5, 3] = np.float32(3.4e38)
+    X[6, 3] = np.float32(-3.4e38)
+    rng = np.random.default_rng(8)
+
+    def chain(depth):
+        node = {"LeafNode": -1.5}
+        for k in range(depth):
+            fid = int(rng.integers(0, 9))
+            node = {"FeatureSplit": {"fid": fid, "split": float(rng.choice(X[:, fid])),
+                                     "lhs": {"LeafNode": float(k)} if k % 2 else node,
+                                     "rhs": node if k % 2 else {"LeafNode": float(-k)}}}
+        return node
+
+    def bushy(depth):
+        if depth == 0 or rng.random() < 0.2:
+            return {"LeafNode": float(np.round(rng.normal(), 4))}
+        fid = int(rng.integers(0, 11))
+        split = float(rng.choice(X[:, fid])) if fid < 9 else float(rng.normal())
+        return {"FeatureSplit": {"fid": fid, "split": split, "lhs": bushy(depth - 1), "rhs": bushy(depth - 1)}}
+
+    shallow = [{"DecisionTree": bushy(d)} for d in (0, 1, 2, 5, 7, 7, 3)]
+    deep = shallow + [{"DecisionTree": chain(14)}]
+    specs = [
+        {"DecisionTree": {"LeafNode": 2.25}},
+        shallow[4],
+        {"Ensemble": {"weights": [float(v) for v in rng.normal(size=len(shallow))], "models": shallow}},
+        {"Ensemble": {"weights": [float(v) for v in rng.normal(size=len(deep))], "models": deep}},
+        {"DecisionTree": chain(14)},
+    ]
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    for env in ({}, {"FASTRANK_NO_HEAP_FOREST": "1"}, {"FASTRANK_NO_FOREST_KERNEL": "1"}):
+        for k in ("FASTRANK_NO_HEAP_FOREST", "FASTRANK_NO_FOREST_KERNEL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for spec in specs:
+            got = fr.CModel.from_dict(spec).predict_dense(ds)
+            assert np.array_equal(got, oracle.score_model(X, spec)), (env, list(spec)[0])
