@@ -197,9 +197,8 @@ struct Forest {
     DevBuf<uint4> nodes;       // .x fid (FR_LEAF: leaf)  .y split (f32 bits)  .z/.w children, or leaf f64 lo/hi
     DevBuf<uint32_t> roots;    // first node of every tree
     DevBuf<double> weights;    // ensemble weights
-    DevBuf<uint2> hnodes;      // implicit-heap layout: [tree][2^levels - 1] {fid, split bits}
-    DevBuf<double> hleaves;    //                       [tree][2^levels]
-    uint32_t n_trees = 0, levels = 0, dstage = 1;
+    DevBuf<uint4> heap_blocks; // implicit-heap layout, per tree [2^levels - 1 nodes][pad][2^levels leaves]
+    uint32_t n_trees = 0, levels = 0, dstage = 1, batch = 1;
     bool weighted = false, heap = false;
 };
 

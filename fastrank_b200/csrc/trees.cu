@@ -88,66 +88,94 @@ __global__ void __launch_bounds__(kTile) forest_tile_kernel(const float *__restr
 }
 
 // Same walk over trees stored as implicit heaps (levels <= kHeapLevels): node i has children
-// 2i+1 / 2i+2, 8 bytes per node {fid, split}, leaves in their own f64 array.  Shallow leaves are
-// padded down to the last level (always-left dummy splits over copies of the leaf value), so
-// every walk takes exactly `levels` steps with no leaf test, and the nodes a warp touches at one
-// level are contiguous: ~4x fewer L1 wavefronts per walk than the 16-byte pointer layout.
+// 2i+1 / 2i+2, 8 bytes per node {fid, split}; a tree is one contiguous block
+//   [2^levels - 1 nodes][1 pad][2^levels f64 leaves]  =  2^(levels+4) bytes.
+// Shallow leaves are padded down to the last level (always-left dummy splits over copies of the
+// leaf value), so every walk takes exactly `levels` steps with no leaf test.  Trees are streamed
+// through shared memory in batches with double-buffered cp.async, so a walk never waits on L2:
+// every step is two shared-memory reads (node, feature) and a compare.
 __global__ void __launch_bounds__(kTile) forest_heap_kernel(const float *__restrict__ x, size_t ld,
                                                             uint32_t dstage, size_t n,
-                                                            const uint2 *__restrict__ hnodes,
-                                                            const double *__restrict__ hleaves,
+                                                            const uint4 *__restrict__ heap,
                                                             const double *__restrict__ weights,
-                                                            uint32_t n_trees, uint32_t levels, int weighted,
+                                                            uint32_t n_trees, uint32_t levels,
+                                                            uint32_t batch, int weighted,
                                                             const uint32_t *__restrict__ inst_of_pos,
                                                             double *__restrict__ out_pos,
                                                             double *__restrict__ out_inst) {
-    extern __shared__ __align__(16) float xs[];  // [dstage][kTile]
+    extern __shared__ __align__(16) float xs[];  // [dstage][kTile], then 2 tree-batch buffers
     const int t = threadIdx.x;
     const size_t p0 = (size_t)blockIdx.x * kTile;
+    const uint32_t tree_u4 = 1u << levels;          // 16-byte units per tree
+    const uint32_t batch_u4 = batch * tree_u4;      // ... per batch buffer
+    uint4 *tbuf = (uint4 *)(xs + (size_t)dstage * kTile);
+    const uint32_t n_batches = (n_trees + batch - 1) / batch;
+    auto stage_batch = [&](uint32_t b) {
+        const uint32_t first = b * batch;
+        const uint32_t cnt = min(batch, n_trees - first) * tree_u4;
+        const uint4 *src = heap + (size_t)first * tree_u4;
+        uint4 *dst = tbuf + (size_t)(b & 1) * batch_u4;
+        for (uint32_t i = t; i < cnt; i += kTile) __pipeline_memcpy_async(dst + i, src + i, 16);
+    };
     {
         const int col = (t & 31) * 4, r0 = t >> 5;
         for (uint32_t f = r0; f < dstage; f += kTile / 32)
             __pipeline_memcpy_async(xs + (size_t)f * kTile + col, x + (size_t)f * ld + p0 + col, 16);
+        stage_batch(0);
         __pipeline_commit();
-        __pipeline_wait_prior(0);
     }
-    __syncthreads();
     const size_t p = p0 + t;
-    if (p >= n) return;
     const float *__restrict__ mine = xs + t;
-    const uint32_t n_internal = (1u << levels) - 1u, n_leaves = 1u << levels;
+    const uint32_t n_internal = tree_u4 * 2 - 1;  // nodes are 8 bytes: 2 per 16-byte unit
     double acc = 0.0;
-    for (uint32_t t0 = 0; t0 < n_trees; t0 += kWalkers) {
-        uint32_t node[kWalkers];
-        const uint2 *base[kWalkers];
-#pragma unroll
-        for (int i = 0; i < kWalkers; ++i) {
-            node[i] = 0;
-            base[i] = hnodes + (size_t)min(t0 + i, n_trees - 1) * n_internal;
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        if (b + 1 < n_batches) {
+            stage_batch(b + 1);
+            __pipeline_commit();
+            __pipeline_wait_prior(1);
+        } else {
+            __pipeline_wait_prior(0);
         }
-        for (uint32_t lvl = 0; lvl < levels; ++lvl) {
-            uint2 w[kWalkers];
-#pragma unroll
-            for (int i = 0; i < kWalkers; ++i) w[i] = __ldg(base[i] + node[i]);
+        __syncthreads();
+        const uint4 *cur = tbuf + (size_t)(b & 1) * batch_u4;
+        const uint32_t first = b * batch, in_batch = min(batch, n_trees - first);
+        for (uint32_t t0 = 0; t0 < in_batch; t0 += kWalkers) {
+            uint32_t node[kWalkers];
+            const uint2 *base[kWalkers];
 #pragma unroll
             for (int i = 0; i < kWalkers; ++i) {
-                const float v = w[i].x < dstage ? mine[(size_t)w[i].x * kTile] : 0.0f;  // model.rs:75
-                node[i] = 2 * node[i] + ((v <= __uint_as_float(w[i].y)) ? 1u : 2u);
+                node[i] = 0;
+                base[i] = (const uint2 *)(cur + (size_t)min(t0 + i, in_batch - 1) * tree_u4);
             }
-        }
+            for (uint32_t lvl = 0; lvl < levels; ++lvl) {
+                uint2 w[kWalkers];
 #pragma unroll
-        for (int i = 0; i < kWalkers; ++i) {
-            if (t0 + i < n_trees) {
-                const double leaf = __ldg(hleaves + (size_t)(t0 + i) * n_leaves + (node[i] - n_internal));
-                if (weighted)
-                    acc = __dadd_rn(acc, __dmul_rn(__ldg(weights + t0 + i), leaf));
-                else
-                    acc = leaf;
+                for (int i = 0; i < kWalkers; ++i) w[i] = base[i][node[i]];
+#pragma unroll
+                for (int i = 0; i < kWalkers; ++i) {
+                    const float v = w[i].x < dstage ? mine[(size_t)w[i].x * kTile] : 0.0f;  // model.rs:75
+                    node[i] = 2 * node[i] + ((v <= __uint_as_float(w[i].y)) ? 1u : 2u);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kWalkers; ++i) {
+                if (t0 + i < in_batch) {
+                    // leaves start one 8-byte slot after the last node
+                    const double leaf = ((const double *)base[i])[node[i] + 1];
+                    if (weighted)
+                        acc = __dadd_rn(acc, __dmul_rn(__ldg(weights + first + t0 + i), leaf));
+                    else
+                        acc = leaf;
+                }
             }
         }
+        __syncthreads();  // the buffer is refilled two batches from now
     }
-    if (out_pos) out_pos[p] = acc;
-    if (out_inst) out_inst[inst_of_pos[p]] = acc;
+    (void)n_internal;
+    if (p < n) {
+        if (out_pos) out_pos[p] = acc;
+        if (out_inst) out_inst[inst_of_pos[p]] = acc;
+    }
 }
 
 }  // namespace
@@ -211,11 +239,12 @@ int build_forest(fr_dev_model *m, const uint64_t *code, size_t n_words) {
     const uint32_t dstage = (uint32_t)std::min<size_t>(ds->d, (size_t)max_fid + 1);
     if ((size_t)dstage * kTile * sizeof(float) > 200 * 1024) return 0;  // does not fit: interpreter
     if (weights.empty()) weights.push_back(1.0);
-    fo.heap = levels <= (uint32_t)kHeapLevels && !getenv("FASTRANK_NO_HEAP_FOREST");
+    fo.heap = levels <= (uint32_t)kHeapLevels && !getenv("FASTRANK_NO_HEAP_FOREST") &&
+              (size_t)dstage * kTile * sizeof(float) + 2 * 16 * 1024 <= 220 * 1024;
     if (fo.heap) {
-        const uint32_t n_internal = (1u << levels) - 1u, n_leaves = 1u << levels;
-        std::vector<uint2> hn((size_t)roots.size() * std::max(n_internal, 1u));
-        std::vector<double> hl((size_t)roots.size() * n_leaves);
+        // per tree: [2^levels - 1 nodes][pad][2^levels leaves], 8 bytes each
+        const uint32_t n_internal = (1u << levels) - 1u, slots = 2u << levels;
+        std::vector<uint64_t> hp((size_t)roots.size() * slots, 0);
         const float inf = std::numeric_limits<float>::infinity();
         uint32_t inf_bits;
         memcpy(&inf_bits, &inf, 4);
@@ -224,31 +253,33 @@ int build_forest(fr_dev_model *m, const uint64_t *code, size_t n_words) {
         };
         std::vector<Item> stack;
         for (size_t tr = 0; tr < roots.size(); ++tr) {
-            uint2 *tn = hn.data() + tr * n_internal;
-            double *tl = hl.data() + tr * n_leaves;
+            uint64_t *tp = hp.data() + tr * slots;
             stack.push_back({roots[tr], 0u, 0u});
             while (!stack.empty()) {
                 const Item it = stack.back();
                 stack.pop_back();
                 const uint4 nd = nodes[it.src];
-                if (it.depth == levels) {  // a leaf slot of the heap
-                    const uint64_t bits = (uint64_t)nd.z | ((uint64_t)nd.w << 32);
-                    memcpy(&tl[it.heap - n_internal], &bits, 8);
+                if (it.depth == levels) {  // a leaf slot of the heap (nd is a leaf here)
+                    tp[it.heap + 1] = (uint64_t)nd.z | ((uint64_t)nd.w << 32);
                     continue;
                 }
                 if (nd.x == frb::FR_LEAF) {  // shallow leaf: pad with an always-left split
-                    tn[it.heap] = make_uint2(0u, inf_bits);
+                    tp[it.heap] = (uint64_t)0u | ((uint64_t)inf_bits << 32);
                     stack.push_back({it.src, 2 * it.heap + 1, it.depth + 1});
                     stack.push_back({it.src, 2 * it.heap + 2, it.depth + 1});
                 } else {
-                    tn[it.heap] = make_uint2(nd.x, nd.y);
+                    tp[it.heap] = (uint64_t)nd.x | ((uint64_t)nd.y << 32);
                     stack.push_back({nd.z, 2 * it.heap + 1, it.depth + 1});
                     stack.push_back({nd.w, 2 * it.heap + 2, it.depth + 1});
                 }
             }
         }
-        CU(fo.hnodes.upload(hn));
-        CU(fo.hleaves.upload(hl));
+        (void)n_internal;
+        std::vector<uint4> packed(hp.size() / 2);
+        memcpy(packed.data(), hp.data(), hp.size() * 8);
+        CU(fo.heap_blocks.upload(packed));
+        const uint32_t tree_bytes = 16u << levels;
+        fo.batch = std::max<uint32_t>(1, (16u * 1024u) / tree_bytes);
     }
     CU(fo.nodes.upload(nodes));
     CU(fo.roots.upload(roots));
@@ -270,12 +301,13 @@ int launch_forest(fr_dev_dataset *ds, const fr_dev_model *m, double *out_pos, do
         CU(cudaFuncSetAttribute(forest_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((ds->n + kTile - 1) / kTile);
     if (fo.heap) {
-        if (smem > 48 * 1024)
-            CU(cudaFuncSetAttribute(forest_heap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        forest_heap_kernel<<<grid, kTile, smem, stream>>>(ds->x.p, ds->ld, fo.dstage, ds->n, fo.hnodes.p,
-                                                          fo.hleaves.p, fo.weights.p, fo.n_trees, fo.levels,
-                                                          fo.weighted ? 1 : 0, ds->inst_of_pos_dev.p, out_pos,
-                                                          out_inst);
+        const size_t hsmem = smem + 2 * (size_t)fo.batch * (16u << fo.levels);
+        if (hsmem > 48 * 1024)
+            CU(cudaFuncSetAttribute(forest_heap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+        forest_heap_kernel<<<grid, kTile, hsmem, stream>>>(ds->x.p, ds->ld, fo.dstage, ds->n, fo.heap_blocks.p,
+                                                           fo.weights.p, fo.n_trees, fo.levels, fo.batch,
+                                                           fo.weighted ? 1 : 0, ds->inst_of_pos_dev.p, out_pos,
+                                                           out_inst);
         LAUNCHED();
         CU(cudaGetLastError());
         return 0;
