@@ -36,7 +36,7 @@ namespace {
 
 constexpr int kMaxSweeps = 8;  // sweeps sharing one pass over X (one blockIdx.y group)
 constexpr int kMaxRows = kMaxSweeps * 32;
-constexpr int kSmemTbl = 256;  // discount-table entries kept in shared memory
+constexpr int kSmemTbl = 64;   // discount-table entries kept in shared memory
 constexpr double kFx = 1099511627776.0;
 static_assert(FR_FX_BITS == 40, "kFx must match FR_FX_BITS");
 
@@ -85,20 +85,21 @@ struct SlotType<256> {
 };
 
 struct SmemLayout {
-    size_t score, roww, sum, tbl, gexp, slot0, slot1, tasks, cls, rowsw, misc, total;
-    __host__ __device__ SmemLayout(int tb, int slot_bytes) {
+    size_t score, roww, sum, tbl, gexp, slot0, slot1, tasks, cls, rowsw, misc, w, total;
+    __host__ __device__ SmemLayout(int tb, int slot_bytes, uint32_t w_doubles) {
         size_t o = 0;
         score = o;  o += align16(sizeof(double) * 32 * (size_t)(tb + 1));
-        roww = o;   o += sizeof(double) * kMaxRows;
+        roww = o;
         sum = o;    o += sizeof(unsigned long long) * kMaxRows;
-        tbl = o;    o += sizeof(double) * kSmemTbl;
-        gexp = o;   o += sizeof(double) * tb;
+        tbl = o;    // the discount table and the per-document gains are never live together
+        gexp = o;   o += sizeof(double) * (tb > kSmemTbl ? tb : kSmemTbl);
         slot0 = o;  o += align16((size_t)slot_bytes * tb * 32);
         slot1 = o;  o += align16((size_t)slot_bytes * tb * 32);
         tasks = o;  o += sizeof(uint2) * tb;
         cls = o;    o += align16(tb);
         rowsw = o;  o += kMaxRows;
         misc = o;   o += 256;
+        w = o;      o += sizeof(double) * w_doubles;  // the weight table, when it is staged
         total = o;
     }
 };
@@ -106,8 +107,8 @@ struct SmemLayout {
 // misc words
 enum { M_F = 0, M_CTR = 18, M_SWROW = 20 /* 9 entries */ };
 
-template <int TB, int TD>
-__global__ void __launch_bounds__(TB, (TB == 128 ? 4 : 1))
+template <int TB, int TD, bool WS>
+__global__ void __launch_bounds__(TB, (TB == 128 ? (WS ? 4 : 5) : 1))
 sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename SlotType<TB>::type slot_t;
@@ -120,9 +121,9 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     const uint32_t row0 = A.grp_row_off[blockIdx.y];
     const int R = (int)(A.grp_row_off[blockIdx.y + 1] - row0);  // rows of this sweep group
     const int G = (R + 31) >> 5;
-    const SmemLayout L(TB, (int)sizeof(slot_t));
+    const uint32_t dm8 = (dm + 7) & ~7u;
+    const SmemLayout L(TB, (int)sizeof(slot_t), WS ? dm8 * NS : 0u);
     double *s_score = (double *)(smem_raw + L.score);  // [32][ROW]
-    double *s_roww = (double *)(smem_raw + L.roww);
     unsigned long long *s_sum = (unsigned long long *)(smem_raw + L.sum);
     double *s_tbl = (double *)(smem_raw + L.tbl);
     double *s_gexp = (double *)(smem_raw + L.gexp);
@@ -132,18 +133,21 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     uint8_t *s_cls = (uint8_t *)(smem_raw + L.cls);
     uint8_t *s_rowsw = (uint8_t *)(smem_raw + L.rowsw);
     int *s_misc = (int *)(smem_raw + L.misc);
+    const double *__restrict__ wg = A.base_wt + (size_t)blockIdx.y * dm8 * NS;
+    double *s_w = (double *)(smem_raw + L.w);
     const bool use_tbl = F.disc_tbl != nullptr;
     const bool tbl_in_smem = use_tbl && F.n_cls * F.tbl_r <= (uint32_t)kSmemTbl;
     const double *tbl = tbl_in_smem ? s_tbl : F.disc_tbl;
 
     // ---- per-launch setup ----
     for (int idx = t; idx < kMaxRows; idx += TB) {
-        s_roww[idx] = idx < R ? A.row_w[row0 + idx] : 0.0;
         s_rowsw[idx] = idx < R ? (uint8_t)A.row_meta[row0 + idx] : (uint8_t)0;
         s_sum[idx] = 0ull;
     }
     if (tbl_in_smem)
         for (uint32_t idx = t; idx < F.n_cls * F.tbl_r; idx += TB) s_tbl[idx] = F.disc_tbl[idx];
+    if (WS)
+        for (uint32_t idx = t; idx < dm8 * NS; idx += TB) s_w[idx] = wg[idx];
     if (t == 0) {
         // first row of every sweep (rows are sorted by sweep), and the coordinates that split a sum
         int r = 0;
@@ -162,8 +166,7 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     for (int s = 0; s < NS; ++s) fs[s] = (uint32_t)s_misc[M_F + s];
     int nan_seen = 0;
     const double *myrow = s_score + (size_t)lane * ROW;
-    const uint32_t dm8 = (dm + 7) & ~7u;
-    const double *__restrict__ wg = A.base_wt + (size_t)blockIdx.y * dm8 * NS;
+
 
     for (uint32_t tile = blockIdx.x; tile < P.nt; tile += gridDim.x) {
         const uint32_t doc0 = P.tile_doc_off[tile];
@@ -206,10 +209,11 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const double xd = (double)cur[u];
-                    const double2 *__restrict__ wj = (const double2 *)(wg + (size_t)(j0 + u) * NS);
+                    const double2 *__restrict__ wj =
+                        (const double2 *)((WS ? (const double *)s_w : wg) + (size_t)(j0 + u) * NS);
 #pragma unroll
                     for (int s = 0; s < NS; s += 2) {
-                        const double2 w2 = __ldg(wj + (s >> 1));
+                        const double2 w2 = WS ? wj[s >> 1] : __ldg(wj + (s >> 1));
                         acc[s] = __dadd_rn(acc[s], __dmul_rn(xd, w2.x));
                         acc[s + 1] = __dadd_rn(acc[s + 1], __dmul_rn(xd, w2.y));
                     }
@@ -237,9 +241,9 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
                     }
                 }
                 const double xs = (double)xs32;
-#pragma unroll 4
+#pragma unroll 8
                 for (; r < seg_end; ++r) {
-                    const double sc = __dadd_rn(ss, __dmul_rn(xs, s_roww[r]));
+                    const double sc = __dadd_rn(ss, __dmul_rn(xs, __ldg(A.row_w + row0 + r)));
                     if (sc != sc) nan_seen |= active ? 1 : 0;
                     col[(size_t)(r - rbeg) * ROW] = sc;
                 }
@@ -391,10 +395,11 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
         atomicAdd((unsigned long long *)(A.sums + A.row_out[row0 + idx]), s_sum[idx]);
 }
 
-template <int TB, int TD>
+template <int TB, int TD, bool WS>
 int launch_fast(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStream_t stream) {
-    const SmemLayout L(TB, (int)sizeof(typename SlotType<TB>::type));
-    auto kernel = sweep_fast_kernel<TB, TD>;
+    const uint32_t dm8 = (a.dm + 7) & ~7u;
+    const SmemLayout L(TB, (int)sizeof(typename SlotType<TB>::type), WS ? dm8 * kMaxSweeps : 0u);
+    auto kernel = sweep_fast_kernel<TB, TD, WS>;
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TB, L.total));
@@ -434,8 +439,8 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
         fp.why = "a query has more than 256 documents";
         return 0;
     }
-    int td = 4;
-    if (const char *env = getenv("FASTRANK_TD")) td = atoi(env) == 8 ? 8 : 4;
+    int td = 8;
+    if (const char *env = getenv("FASTRANK_TD")) td = atoi(env) == 4 ? 4 : 8;
     fp.td = td;
     const bool ndcg = pl->metric == FR_METRIC_NDCG;
     // gain classes
@@ -609,11 +614,21 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         a.dm = (uint32_t)std::min<size_t>(wlen, ds->d);
         a.err = pl->err_dev.p;
         if (pl->nt == 0) continue;
+        // the weight table is staged in shared memory while that costs no resident CTA
+        bool ws = (size_t)((a.dm + 7) & ~7u) * kMaxSweeps * sizeof(double) <= 10 * 1024;
+        if (const char *env = getenv("FASTRANK_WSMEM")) ws = atoi(env) != 0;
         int rc;
-        if (pl->tb == 128)
-            rc = fp.td == 8 ? launch_fast<128, 8>(pl, a, n_groups, s) : launch_fast<128, 4>(pl, a, n_groups, s);
-        else
-            rc = fp.td == 8 ? launch_fast<256, 8>(pl, a, n_groups, s) : launch_fast<256, 4>(pl, a, n_groups, s);
+        if (pl->tb == 128) {
+            if (ws)
+                rc = fp.td == 8 ? launch_fast<128, 8, true>(pl, a, n_groups, s)
+                                : launch_fast<128, 4, true>(pl, a, n_groups, s);
+            else
+                rc = fp.td == 8 ? launch_fast<128, 8, false>(pl, a, n_groups, s)
+                                : launch_fast<128, 4, false>(pl, a, n_groups, s);
+        } else {
+            rc = fp.td == 8 ? launch_fast<256, 8, false>(pl, a, n_groups, s)
+                            : launch_fast<256, 4, false>(pl, a, n_groups, s);
+        }
         if (rc) return 1;
     }
     if (allreduce_sums(pl, pl->sums_dev.p, total, s)) return 1;
