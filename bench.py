@@ -299,7 +299,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         bytes_per_launch = (n_local * d * 4 + n_local * 5 + nq_local * 16 + N_RESTARTS * d * 8
                             + N_RESTARTS * 26 * 16)
-        kname = "sweep_fast_kernel<128,4>"
+        kname = "sweep_fast_kernel<128,8,true>"
     avg_launch_ms = kern_ms / max(n_kern, 1)
     achieved = bytes_per_launch / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else 0.0
     peak, peak_src = measured_peak_gbs()
@@ -320,13 +320,18 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     t0 = time.perf_counter()
     ds = fr.CDataset.from_numpy(Xl, yl, ql)
+    t_from_numpy = time.perf_counter() - t0
     req = fr.TrainRequest.coordinate_ascent()
     req.measure = "ndcg@%d" % DEPTH
     req.params.num_restarts = N_RESTARTS
     req.params.seed = 42
     req.params.quiet = True
+    t1 = time.perf_counter()
     model = ds.train_model(req)
+    t_train = time.perf_counter() - t1
+    t1 = time.perf_counter()
     final = ds.evaluate_mean(model, req.measure)
+    t_eval = time.perf_counter() - t1
     barrier()
     e2e_s = time.perf_counter() - t0
     stats = fr.query_json("last_train_stats")
@@ -341,6 +346,7 @@ def run_ours(args, rank, world, local_rank):
            "d2h_bytes_per_step": d2h_total / max(stats["global_steps"], 1),
            "seconds": e2e_s, "evals_consumed": stats["evals_consumed"], "evals_computed": stats["evals_computed"],
            "global_steps": stats["global_steps"], "final_train_ndcg10": final,
+           "seconds_from_numpy": t_from_numpy, "seconds_train_model": t_train, "seconds_evaluate": t_eval,
            "what": "from_numpy + train_model(CA, 8 restarts, seed 42, to convergence) + evaluate through the C ABI"}
     del ds, model
     clocks = sampler.stop()  # sampled across both timed regions (device-timed steps and e2e)
@@ -381,7 +387,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exact", action="store_true", help="time the exact-order sweep kernel instead of the batched one")
-    ap.add_argument("--cpu-evals-per-thread", type=int, default=4)
+    ap.add_argument("--cpu-evals-per-thread", type=int, default=60,
+                    help="bounded CPU sample: evaluations per host thread (8 threads x 60 ~ 10 s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
