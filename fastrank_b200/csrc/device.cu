@@ -713,6 +713,7 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
                     std::to_string(kMaxTile) + " per query");
     pl->max_len = max_len;
     int tb = 128;
+    if (const char *env = getenv("FASTRANK_TB")) tb = atoi(env) >= 256 ? 256 : 128;  // tuning knob
     while (tb < (int)max_len) tb *= 2;
     pl->tb = tb;
     // 2. pack whole queries into tiles of <= tb documents, in view order

@@ -249,6 +249,7 @@ struct FastPlan {
     DevBuf<uint32_t> row_meta;       // sweep of the row (index inside its group of 8 sweeps)
     DevBuf<uint32_t> row_out;        // where the row's sum goes: sweep * cand_stride + candidate
     DevBuf<uint32_t> grp_row_off;    // rows of sweep group g: [grp_row_off[g], grp_row_off[g + 1])
+    DevBuf<unsigned> tile_ctr;       // per sweep group: next tile to hand out
 };
 
 struct FastView {

@@ -54,6 +54,7 @@ struct FastArgs {
     double *perq;  // nullptr or [n_out][nq_view]
     uint32_t n_sweeps, wlen;
     uint32_t dm;  // min(wlen, features): zip() truncation of dense_dataset.rs:67-76
+    unsigned *tile_ctr;  // [n_groups] zeroed before the launch: tiles are handed out dynamically
     int *err;
 };
 
@@ -105,10 +106,10 @@ struct SmemLayout {
 };
 
 // misc words
-enum { M_F = 0, M_CTR = 18, M_SWROW = 20 /* 9 entries */ };
+enum { M_F = 0, M_TILE = 16, M_NEXT = 17, M_CTR = 18, M_SWROW = 20 /* 9 entries */ };
 
 template <int TB, int TD, bool WS>
-__global__ void __launch_bounds__(TB, (TB == 128 ? (WS ? 4 : 5) : 1))
+__global__ void __launch_bounds__(TB, (TB == 128 ? (WS ? 4 : 5) : 2))
 sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename SlotType<TB>::type slot_t;
@@ -159,6 +160,7 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
             const bool has_rows = s_misc[M_SWROW + s + 1] > s_misc[M_SWROW + s];
             s_misc[M_F + s] = (s < ns && has_rows) ? (int)A.fid[s0 + s] : -1;
         }
+        s_misc[M_TILE] = (int)atomicAdd(A.tile_ctr + blockIdx.y, 1u);
     }
     __syncthreads();
     uint32_t fs[NS];
@@ -168,7 +170,10 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     const double *myrow = s_score + (size_t)lane * ROW;
 
 
-    for (uint32_t tile = blockIdx.x; tile < P.nt; tile += gridDim.x) {
+    if (G == 0) return;
+    for (uint32_t tile = (uint32_t)s_misc[M_TILE]; tile < P.nt; tile = (uint32_t)s_misc[M_NEXT]) {
+        // the next tile is claimed now; the value is read after this tile's last barrier
+        if (t == 0) s_misc[M_NEXT] = (int)atomicAdd(A.tile_ctr + blockIdx.y, 1u);
         const uint32_t doc0 = P.tile_doc_off[tile];
         const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
         const bool active = t < nd;
@@ -255,7 +260,7 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
             if (t == 0) s_misc[M_CTR] = 0;
         };
 
-        if (G > 0) score_group(0);
+        score_group(0);
         __syncthreads();
         for (int g = 0; g < G; ++g) {
             slot_t *slots = s_slot0 + (size_t)(g & 1) * slot_stride;
@@ -614,6 +619,9 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         a.dm = (uint32_t)std::min<size_t>(wlen, ds->d);
         a.err = pl->err_dev.p;
         if (pl->nt == 0) continue;
+        CU(fp.tile_ctr.ensure(n_groups));
+        CU(cudaMemsetAsync(fp.tile_ctr.p, 0, sizeof(unsigned) * n_groups, s));
+        a.tile_ctr = fp.tile_ctr.p;
         // the weight table is staged in shared memory while that costs no resident CTA
         bool ws = (size_t)((a.dm + 7) & ~7u) * kMaxSweeps * sizeof(double) <= 10 * 1024;
         if (const char *env = getenv("FASTRANK_WSMEM")) ws = atoi(env) != 0;
