@@ -347,6 +347,8 @@ def run_ours(args, rank, world, local_rank):
            "seconds": e2e_s, "evals_consumed": stats["evals_consumed"], "evals_computed": stats["evals_computed"],
            "global_steps": stats["global_steps"], "final_train_ndcg10": final,
            "seconds_from_numpy": t_from_numpy, "seconds_train_model": t_train, "seconds_evaluate": t_eval,
+           "train_seconds_setup": stats.get("seconds_setup"), "train_seconds_device": stats.get("seconds_device"),
+           "sweeps": stats["sweeps"],
            "what": "from_numpy + train_model(CA, 8 restarts, seed 42, to convergence) + evaluate through the C ABI"}
     del ds, model
     clocks = sampler.stop()  # sampled across both timed regions (device-timed steps and e2e)

@@ -11,6 +11,8 @@
 #include <cstring>
 #include <fstream>
 
+#include <chrono>
+
 #include "host.hpp"
 
 using namespace frb;
@@ -241,6 +243,9 @@ const void *query_json(const void *json_cmd_str) {
             o.set("evals_computed", json::Value::uinteger(s.evals_computed));
             o.set("sweeps", json::Value::uinteger(s.sweeps));
             o.set("global_steps", json::Value::uinteger(s.global_steps));
+            o.set("seconds_setup", json::Value::number(s.seconds_setup));
+            o.set("seconds_device", json::Value::number(s.seconds_device));
+            o.set("seconds_total", json::Value::number(s.seconds_total));
             o.set("kernel_launches", json::Value::uinteger(fr_dev_kernel_launches()));
             return json::dump(o);
         }
@@ -276,15 +281,29 @@ const CResult *train_model(void *train_request_json_ptr, void *dataset) {
         const Measure m = Measure::parse(measure->s);  // json_api.rs:40-44
         const std::string &kind = params->obj[0].first;
         TrainStats stats;
+        const auto t_begin = std::chrono::steady_clock::now();
+        auto seconds_since = [&](std::chrono::steady_clock::time_point t0) {
+            return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        };
         if (kind == "CoordinateAscent") {
             const CoordinateAscentParams p = CoordinateAscentParams::from_json(params->obj[0].second);
             Evaluator ev(d.view, m, qrel.get());
-            return new CModel{coordinate_ascent_learn(p, d.view, ev, &stats)};
+            const double setup = seconds_since(t_begin);
+            CModel *out = new CModel{coordinate_ascent_learn(p, d.view, ev, &stats)};
+            stats.seconds_setup = setup;
+            stats.seconds_total = seconds_since(t_begin);
+            set_last_train_stats(stats);
+            return out;
         }
         if (kind == "RandomForest") {
             const RandomForestParams p = RandomForestParams::from_json(params->obj[0].second);
             Evaluator ev(d.view, m, qrel.get());
-            return new CModel{random_forest_learn(p, d.view, ev, &stats)};
+            const double setup = seconds_since(t_begin);
+            CModel *out = new CModel{random_forest_learn(p, d.view, ev, &stats)};
+            stats.seconds_setup = setup;
+            stats.seconds_total = seconds_since(t_begin);
+            set_last_train_stats(stats);
+            return out;
         }
         throw Error("unknown variant `" + kind + "`, expected `CoordinateAscent` or `RandomForest`");
     });

@@ -13,6 +13,7 @@
 // Direction -1 of group A is speculative with respect to the break after direction 0; the
 // statistics keep "consumed" (what the reference's control flow evaluates) and "computed"
 // apart.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -184,6 +185,7 @@ Model coordinate_ascent_learn(const CoordinateAscentParams &p, const DatasetView
         // 2. one GPU pass over the feature matrix for all restarts (batched sweep); the
         //    exact-order kernel (one pass per restart) on request or for very long queries
         sums.assign(active.size() * stride, 0);
+        const auto t_dev = std::chrono::steady_clock::now();
         const int rc = use_fast
                            ? fr_dev_eval_coord_sweeps_fast(ev.plan(), active.size(), base_w.data(), dim,
                                                            fid_arr.data(), cand_w.data(), ncand.data(),
@@ -191,6 +193,7 @@ Model coordinate_ascent_learn(const CoordinateAscentParams &p, const DatasetView
                            : fr_dev_eval_coord_sweeps(ev.plan(), active.size(), base_w.data(), dim,
                                                       fid_arr.data(), cand_w.data(), ncand.data(), stride,
                                                       sums.data());
+        stats.seconds_device += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_dev).count();
         if (rc) throw Error(fr_dev_last_error());
         stats.sweeps += active.size();
         stats.global_steps += 1;

@@ -160,6 +160,7 @@ json::Value QRel::to_json() const {
 // ParentDataset
 // ---------------------------------------------------------------------------------------
 ParentDataset::~ParentDataset() {
+    plan_cache.clear();  // plans reference the device dataset
     if (dev) fr_dev_dataset_destroy(dev);
 }
 

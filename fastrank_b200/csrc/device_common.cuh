@@ -244,12 +244,11 @@ struct FastPlan {
     DevBuf<uint2> tasks;             // .x = qs | qe << 16, .y = t0 | n << 16 (tile-local documents)
     DevBuf<uint8_t> pd_cls;          // plan doc -> gain class
     DevBuf<double> disc_tbl;         // [n_cls][tbl_r]  (2^gain - 1) / log2(r + 2)
-    // per-call work buffers: the call's candidates flattened into rows
-    DevBuf<double> row_w;            // candidate weight of the row
-    DevBuf<uint32_t> row_meta;       // sweep of the row (index inside its group of 8 sweeps)
-    DevBuf<uint32_t> row_out;        // where the row's sum goes: sweep * cand_stride + candidate
-    DevBuf<uint32_t> grp_row_off;    // rows of sweep group g: [grp_row_off[g], grp_row_off[g + 1])
-    DevBuf<unsigned> tile_ctr;       // per sweep group: next tile to hand out
+    // per-call work buffers (sweep_fast.cu documents the layout): one input blob = transposed
+    // weights + the call's candidates flattened into rows, one output blob = sums, error flags,
+    // tile counters; each moves with a single copy through pinned memory
+    DevBuf<unsigned char> in_dev, out_dev;
+    PinnedBuf<unsigned char> in_host, out_host;
 };
 
 struct FastView {

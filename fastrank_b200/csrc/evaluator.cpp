@@ -56,6 +56,7 @@ Evaluator::Evaluator(const DatasetView &view, const Measure &measure, const QRel
     : view_(view), measure_(measure) {
     ParentDataset &parent = *view.parent;
     fr_dev_dataset *dev = parent.device();
+    use_lock_ = std::unique_lock<std::recursive_mutex>(parent.use_mu);
     const auto groups = view.instances_by_query();
     std::vector<uint64_t> inst_off{0};
     std::vector<uint32_t> inst_ids;
@@ -68,6 +69,19 @@ Evaluator::Evaluator(const DatasetView &view, const Measure &measure, const QRel
         for (const auto &g : groups) {
             inst_ids.insert(inst_ids.end(), g.second.begin(), g.second.end());
             inst_off.push_back(inst_ids.size());
+        }
+    }
+    // a plan built earlier for the same view and measure (no judgments involved) is reused
+    fr_dev_comm *const comm_now = fr_dev_default_comm();
+    const bool cacheable = !(qrel && measure.metric != FR_METRIC_RR);
+    if (cacheable) {
+        for (const std::shared_ptr<PlanHolder> &h : parent.plan_cache) {
+            if (h->metric == measure.metric && h->depth == measure.depth && h->comm == comm_now &&
+                h->sampled == view.sampled && (!view.sampled || h->instances == view.instances)) {
+                holder_ = h;
+                plan_ = h->plan;
+                return;
+            }
         }
     }
     std::vector<uint8_t> present;
@@ -97,20 +111,24 @@ Evaluator::Evaluator(const DatasetView &view, const Measure &measure, const QRel
     desc.inst_ids = subset ? inst_ids.data() : nullptr;
     desc.norm_present = present.empty() ? nullptr : present.data();
     desc.norm_value = value.empty() ? nullptr : value.data();
-    if (fr_dev_plan_create(dev, &desc, &plan_)) throw Error(fr_dev_last_error());
-    if (fr_dev_comm *comm = fr_dev_default_comm()) {
-        if (fr_dev_plan_set_comm(plan_, comm)) {
-            const std::string why = fr_dev_last_error();
-            fr_dev_plan_destroy(plan_);
-            plan_ = nullptr;
-            throw Error(why);
-        }
+    holder_ = std::make_shared<PlanHolder>();
+    if (fr_dev_plan_create(dev, &desc, &holder_->plan)) throw Error(fr_dev_last_error());
+    plan_ = holder_->plan;
+    if (comm_now) {
+        if (fr_dev_plan_set_comm(plan_, comm_now)) throw Error(fr_dev_last_error());
+    }
+    if (cacheable) {
+        holder_->metric = measure.metric;
+        holder_->depth = measure.depth;
+        holder_->sampled = view.sampled;
+        if (view.sampled) holder_->instances = view.instances;
+        holder_->comm = comm_now;
+        if (parent.plan_cache.size() >= 8) parent.plan_cache.erase(parent.plan_cache.begin());
+        parent.plan_cache.push_back(holder_);
     }
 }
 
-Evaluator::~Evaluator() {
-    if (plan_) fr_dev_plan_destroy(plan_);
-}
+Evaluator::~Evaluator() {}
 
 double Evaluator::mean_from_fx(int64_t fx) const {
     const uint64_t nq = global_queries();

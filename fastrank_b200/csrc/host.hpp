@@ -103,6 +103,20 @@ struct Model {
 // ----------------------------------------------------------------------------------------
 // Datasets (dense_dataset.rs, dataset.rs, instance.rs, libsvm.rs, sampling.rs)
 // ----------------------------------------------------------------------------------------
+// A device plan kept by its dataset so that repeated evaluations of the same (view, measure)
+// -- train_model followed by evaluate, evaluate in a loop -- do not rebuild it.
+struct PlanHolder {
+    fr_dev_plan *plan = nullptr;
+    int metric = 0;
+    int64_t depth = -1;
+    bool sampled = false;
+    std::vector<uint32_t> instances;  // the view's instances when sampled
+    fr_dev_comm *comm = nullptr;
+    ~PlanHolder() {
+        if (plan) fr_dev_plan_destroy(plan);
+    }
+};
+
 struct ParentDataset {
     size_t n = 0;
     size_t d = 0;                 // n_dim: row length of the dense matrix
@@ -122,6 +136,8 @@ struct ParentDataset {
 
     std::mutex dev_mu;
     fr_dev_dataset *dev = nullptr;             // uploaded on first use
+    std::recursive_mutex use_mu;               // one evaluator at a time drives the device state
+    std::vector<std::shared_ptr<PlanHolder>> plan_cache;  // plans without judgments, newest last
 
     ~ParentDataset();
     fr_dev_dataset *device();                  // throws Error when no GPU is usable
@@ -181,6 +197,8 @@ class Evaluator {
     DatasetView view_;
     Measure measure_;
     std::vector<uint32_t> view_queries_;
+    std::unique_lock<std::recursive_mutex> use_lock_;
+    std::shared_ptr<PlanHolder> holder_;
     fr_dev_plan *plan_ = nullptr;
 };
 
@@ -224,6 +242,9 @@ struct TrainStats {
     uint64_t evals_computed = 0;  // candidates actually scored on the GPU (speculation included)
     uint64_t sweeps = 0;
     uint64_t global_steps = 0;
+    double seconds_setup = 0.0;   // evaluator construction: dataset upload (first use) + plan
+    double seconds_device = 0.0;  // inside the fr_dev_* evaluation calls (copies, kernels, sync)
+    double seconds_total = 0.0;   // the whole train_model call
 };
 
 Model coordinate_ascent_learn(const CoordinateAscentParams &p, const DatasetView &view,

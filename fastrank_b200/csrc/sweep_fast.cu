@@ -547,81 +547,85 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
     for (size_t r = 0; r < n_sweeps; ++r)
         if (n_cand[r] > cand_stride) return fail("fr_dev_eval_coord_sweeps_fast: n_cand > cand_stride");
     const uint32_t n_groups = (uint32_t)((n_sweeps + kMaxSweeps - 1) / kMaxSweeps);
-    CU(pl->fid_dev.ensure(n_sweeps));
-    CU(pl->sums_dev.ensure(total));
-    CU(pl->sums_host.ensure(total));
+    const size_t dm = std::min<size_t>(wlen, ds->d);
+    const size_t dm8 = std::max<size_t>((dm + 7) & ~(size_t)7, 8);
+    const size_t wt_count = (size_t)n_groups * dm8 * kMaxSweeps;
+    const size_t max_rows = std::min<size_t>(total, (size_t)n_groups * kMaxRows);
+    // One pinned staging blob -> one H2D copy per pass:
+    //   [wt doubles][row_w doubles][fid u32][row_meta u32][row_out u32][grp_off u32]
+    const size_t in_bytes = sizeof(double) * (wt_count + max_rows) +
+                            sizeof(uint32_t) * (n_sweeps + 2 * max_rows + n_groups + 1);
+    // One device blob cleared with one memset and read back with one D2H copy:
+    //   [sums i64 x total][err i32][pad i32][tile counters u32 x n_groups]
+    const size_t out_bytes = sizeof(long long) * total + 8 + sizeof(unsigned) * n_groups;
+    CU(fp.in_dev.ensure(in_bytes));
+    CU(fp.in_host.ensure(in_bytes));
+    CU(fp.out_dev.ensure(out_bytes));
+    CU(fp.out_host.ensure(sizeof(long long) * total + 8));
     if (out_per_query) CU(pl->perq_dev.ensure(total * (size_t)pl->nq_view));
-    {
-        // base weights transposed per sweep group: wt[g][j][s]; unused sweep columns are zero
-        const size_t dm = std::min<size_t>(wlen, ds->d);
-        const size_t dm8 = (dm + 7) & ~(size_t)7;
-        std::vector<double> wt((size_t)n_groups * std::max<size_t>(dm8, 8) * kMaxSweeps, 0.0);
-        for (size_t sw = 0; sw < n_sweeps; ++sw)
-            for (size_t j = 0; j < dm; ++j)
-                wt[((sw / kMaxSweeps) * dm8 + j) * kMaxSweeps + sw % kMaxSweeps] =
-                    j == fid[sw] ? 0.0 : base_w[sw * wlen + j];
-        CU(pl->w_dev.ensure(wt.size()));
-        CU(cudaMemcpyAsync(pl->w_dev.p, wt.data(), sizeof(double) * wt.size(), cudaMemcpyHostToDevice, s));
-    }
-    CU(cudaMemcpyAsync(pl->fid_dev.p, fid, sizeof(uint32_t) * n_sweeps, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(pl->sums_dev.p, 0, sizeof(long long) * total, s));
-    CU(cudaMemsetAsync(pl->err_dev.p, 0, sizeof(int), s));
+    long long *sums_dev = (long long *)fp.out_dev.p;
+    int *err_dev = (int *)(fp.out_dev.p + sizeof(long long) * total);
+    unsigned *ctr_dev = (unsigned *)(fp.out_dev.p + sizeof(long long) * total + 8);
+    CU(cudaMemsetAsync(fp.out_dev.p, 0, out_bytes, s));
     if (out_per_query)
         CU(cudaMemsetAsync(pl->perq_dev.p, 0, sizeof(double) * total * (size_t)pl->nq_view, s));
-    std::vector<double> row_w;
-    std::vector<uint32_t> row_meta, row_out, grp_off;
+    bool first_pass = true;
     for (;;) {
-        row_w.clear();
-        row_meta.clear();
-        row_out.clear();
-        grp_off.assign(1, 0);
+        if (!first_pass) CU(cudaStreamSynchronize(s));  // the staging blob is about to be rewritten
+        unsigned char *hp = fp.in_host.p;
+        double *h_wt = (double *)hp;
+        double *h_row_w = h_wt + wt_count;
+        uint32_t *h_fid = (uint32_t *)(h_row_w + max_rows);
+        uint32_t *h_row_meta = h_fid + n_sweeps;
+        uint32_t *h_row_out = h_row_meta + max_rows;
+        uint32_t *h_grp = h_row_out + max_rows;
+        size_t nrows = 0;
+        h_grp[0] = 0;
         bool any = false;
         for (uint32_t g = 0; g < n_groups; ++g) {
             const size_t sw0 = (size_t)g * kMaxSweeps, sw1 = std::min(n_sweeps, sw0 + kMaxSweeps);
             uint32_t room = kMaxRows;
             for (size_t sw = sw0; sw < sw1 && room > 0; ++sw) {
                 while (cursor[sw] < n_cand[sw] && room > 0) {
-                    row_w.push_back(cand_w[sw * cand_stride + cursor[sw]]);
-                    row_meta.push_back((uint32_t)(sw - sw0));
-                    row_out.push_back((uint32_t)(sw * cand_stride + cursor[sw]));
+                    h_row_w[nrows] = cand_w[sw * cand_stride + cursor[sw]];
+                    h_row_meta[nrows] = (uint32_t)(sw - sw0);
+                    h_row_out[nrows] = (uint32_t)(sw * cand_stride + cursor[sw]);
+                    ++nrows;
                     ++cursor[sw];
                     --room;
                     any = true;
                 }
             }
-            grp_off.push_back((uint32_t)row_w.size());
+            h_grp[g + 1] = (uint32_t)nrows;
         }
         if (!any) break;
-        // (copies from pageable memory are staged before cudaMemcpyAsync returns, and the device
-        // buffers are overwritten in stream order behind the previous pass)
-        CU(fp.row_w.ensure(row_w.size()));
-        CU(fp.row_meta.ensure(row_meta.size()));
-        CU(fp.row_out.ensure(row_out.size()));
-        CU(fp.grp_row_off.ensure(grp_off.size()));
-        CU(cudaMemcpyAsync(fp.row_w.p, row_w.data(), sizeof(double) * row_w.size(), cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(fp.row_meta.p, row_meta.data(), sizeof(uint32_t) * row_meta.size(),
-                           cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(fp.row_out.p, row_out.data(), sizeof(uint32_t) * row_out.size(),
-                           cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(fp.grp_row_off.p, grp_off.data(), sizeof(uint32_t) * grp_off.size(),
-                           cudaMemcpyHostToDevice, s));
+        // base weights transposed per sweep group: wt[g][j][s]; unused sweep columns stay zero,
+        // and so does the coordinate each sweep varies
+        memset(h_wt, 0, sizeof(double) * wt_count);
+        for (size_t sw = 0; sw < n_sweeps; ++sw) {
+            double *col = h_wt + (sw / kMaxSweeps) * dm8 * kMaxSweeps + sw % kMaxSweeps;
+            for (size_t j = 0; j < dm; ++j) col[j * kMaxSweeps] = j == fid[sw] ? 0.0 : base_w[sw * wlen + j];
+            h_fid[sw] = fid[sw];
+        }
+        CU(cudaMemcpyAsync(fp.in_dev.p, hp, in_bytes, cudaMemcpyHostToDevice, s));
+        if (!first_pass) CU(cudaMemsetAsync(ctr_dev, 0, sizeof(unsigned) * n_groups, s));
+        first_pass = false;
+        unsigned char *dp = fp.in_dev.p;
         FastArgs a;
-        a.base_wt = pl->w_dev.p;
-        a.fid = pl->fid_dev.p;
-        a.row_w = fp.row_w.p;
-        a.row_meta = fp.row_meta.p;
-        a.row_out = fp.row_out.p;
-        a.grp_row_off = fp.grp_row_off.p;
-        a.sums = pl->sums_dev.p;
+        a.base_wt = (const double *)dp;
+        a.row_w = a.base_wt + wt_count;
+        a.fid = (const uint32_t *)(a.row_w + max_rows);
+        a.row_meta = a.fid + n_sweeps;
+        a.row_out = a.row_meta + max_rows;
+        a.grp_row_off = a.row_out + max_rows;
+        a.sums = sums_dev;
         a.perq = out_per_query ? pl->perq_dev.p : nullptr;
         a.n_sweeps = (uint32_t)n_sweeps;
         a.wlen = (uint32_t)wlen;
-        a.dm = (uint32_t)std::min<size_t>(wlen, ds->d);
-        a.err = pl->err_dev.p;
+        a.dm = (uint32_t)dm;
+        a.err = err_dev;
+        a.tile_ctr = ctr_dev;
         if (pl->nt == 0) continue;
-        CU(fp.tile_ctr.ensure(n_groups));
-        CU(cudaMemsetAsync(fp.tile_ctr.p, 0, sizeof(unsigned) * n_groups, s));
-        a.tile_ctr = fp.tile_ctr.p;
         // the weight table is staged in shared memory while that costs no resident CTA
         bool ws = (size_t)((a.dm + 7) & ~7u) * kMaxSweeps * sizeof(double) <= 10 * 1024;
         if (const char *env = getenv("FASTRANK_WSMEM")) ws = atoi(env) != 0;
@@ -639,15 +643,15 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         }
         if (rc) return 1;
     }
-    if (allreduce_sums(pl, pl->sums_dev.p, total, s)) return 1;
-    CU(cudaMemcpyAsync(pl->sums_host.p, pl->sums_dev.p, sizeof(long long) * total,
-                       cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(pl->err_host.p, pl->err_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (allreduce_sums(pl, sums_dev, total, s)) return 1;
+    CU(cudaMemcpyAsync(fp.out_host.p, fp.out_dev.p, sizeof(long long) * total + 8, cudaMemcpyDeviceToHost, s));
     if (out_per_query)
         CU(cudaMemcpyAsync(out_per_query, pl->perq_dev.p, sizeof(double) * total * (size_t)pl->nq_view,
                            cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    if (check_err_flags(pl->err_host.p[0])) return 1;
-    for (size_t i = 0; i < total; ++i) out_sum_fx[i] = pl->sums_host.p[i];
+    int err_flags;
+    memcpy(&err_flags, fp.out_host.p + sizeof(long long) * total, sizeof(int));
+    if (check_err_flags(err_flags)) return 1;
+    memcpy(out_sum_fx, fp.out_host.p, sizeof(long long) * total);
     return 0;
 }

@@ -1,0 +1,103 @@
+"""Parity at BASELINE.json's full size (1M documents x 136 features x 30k queries), through
+properties that do not need the oracle on the whole dataset plus an oracle check on a query
+sample:
+  * 400 sampled queries: per-query NDCG@10 of the exact kernels bit-identical to the oracle, and
+    of the batched sweep bit-identical wherever the ranking is (here: everywhere);
+  * batched sweep vs exact-order sweep over ALL queries: integer sums within 1e-9 of each other
+    in the mean;
+  * scale invariance: multiplying a weight vector by a power of two multiplies every score
+    exactly, so rankings -- and the integer metric sums -- must not move;
+  * a line-search candidate equal to the base weight reproduces evaluate_mean of the base;
+  * row-permutation invariance of the mean (sums are order-independent integers).
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import DevDataset, fx_sum, oracle_dataset, synth
+from fastrank_b200.kernels import dense_query_index
+
+pytestmark = pytest.mark.gpu
+
+N, D, Q = 1_000_000, 136, 30_000
+FX = float(1 << 40)
+
+
+@pytest.fixture(scope="module")
+def full():
+    X, y, qid = synth(N, D, Q)
+    qidx, nq = dense_query_index(qid)
+    dev = DevDataset(X, y.astype(np.float32), qidx, nq)
+    yield X, y, qid, dev, nq
+    dev.close()
+
+
+def _line(orig, n):
+    c = [0.0] + [orig - 0.05 * (2.0 ** k - 1) for k in range(1, 40)]
+    return c[:n]
+
+
+def test_full_size_sample_against_oracle_and_invariances(oracle, full):
+    X, y, qid, dev, nq = full
+    rng = np.random.default_rng(11)
+    base = rng.uniform(-1, 1, size=(8, D))
+    base /= np.abs(base).sum(axis=1, keepdims=True)
+    fids = [int(v) for v in rng.integers(0, D, 8)]
+    cands = [_line(base[r, fids[r]], 26) for r in range(8)]
+    plan = dev.plan(0, 10)
+    fast, pq_fast = None, None
+    fast = plan.coord_sweeps(base, fids, cands, fast=True)
+    exact = plan.coord_sweeps(base, fids, cands)
+    # (1) batched vs exact-order sweep on all 30k queries
+    diff = np.abs(fast - exact).astype(np.float64) / FX / nq
+    assert diff.max() < 1e-9, diff.max()
+    # (2) oracle on a sample of queries, per query, for full weight vectors of two candidates
+    uq = np.unique(qid)
+    pick = np.sort(rng.choice(len(uq), 400, replace=False))
+    rows = np.nonzero(np.isin(qid, uq[pick]))[0]
+    Xs, ys, qs = np.ascontiguousarray(X[rows]), y[rows], qid[rows]
+    ods = oracle_dataset(oracle, Xs, ys, qs)
+    W = []
+    for r, k in ((0, 0), (3, 7), (7, 25)):
+        w = base[r].copy()
+        w[fids[r]] = cands[r][k]
+        W.append(w)
+    W = np.asarray(W)
+    sums_lin, pq_lin = plan.eval_linear(W)
+    qpos = {int(v): i for i, v in enumerate(uq)}  # dense query index == order of first appearance (qid sorted)
+    for c in range(len(W)):
+        exp = oracle.evaluate_scores(ods, oracle.score_linear(Xs, W[c]), "ndcg@10")
+        got = pq_lin[c][[qpos[int(v)] for v in uq[pick]]]
+        assert np.array_equal(got, exp)
+    for c, (r, k) in enumerate(((0, 0), (3, 7), (7, 25))):
+        assert int(exact[r, k]) == int(sums_lin[c])          # exact sweep == full rescoring
+        assert abs(int(fast[r, k]) - int(sums_lin[c])) / FX / nq < 1e-9
+    # (3) scale invariance (exact power-of-two scaling)
+    s4, _ = plan.eval_linear(W * 4.0, per_query=False)
+    s8, _ = plan.eval_linear(W * 0.125, per_query=False)
+    assert s4.tolist() == sums_lin.tolist() and s8.tolist() == sums_lin.tolist()
+    # (4) a candidate equal to the base weight reproduces the base's evaluate_mean
+    same = plan.coord_sweeps(base[:2], fids[:2], [[base[0, fids[0]]], [base[1, fids[1]]]], fast=True)
+    base_sums, _ = plan.eval_linear(base[:2], per_query=False)
+    assert abs(int(same[0, 0]) - int(base_sums[0])) / FX / nq < 1e-9
+    assert abs(int(same[1, 0]) - int(base_sums[1])) / FX / nq < 1e-9
+
+
+def test_full_size_row_permutation_invariance(full):
+    X, y, qid, dev, nq = full
+    rng = np.random.default_rng(12)
+    n = 200_000  # a 200k-row prefix (whole queries), permuted
+    cut = int(np.searchsorted(qid, qid[n]))
+    Xa, ya, qa = X[:cut], y[:cut], qid[:cut]
+    perm = rng.permutation(cut)
+    W = rng.normal(size=(2, D))
+    out = []
+    for Xi, yi, qi in ((Xa, ya, qa), (np.ascontiguousarray(Xa[perm]), ya[perm], qa[perm])):
+        qidx, nq_i = dense_query_index(qi)
+        d2 = DevDataset(Xi, yi.astype(np.float32), qidx, nq_i)
+        try:
+            sums, _ = d2.plan(0, 10).eval_linear(W, per_query=False)
+            out.append(sums.tolist())
+        finally:
+            d2.close()
+    # random float features: no score ties inside a query, so the id tie-break cannot matter
+    assert out[0] == out[1]
