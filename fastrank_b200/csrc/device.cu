@@ -686,7 +686,8 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
     }
     // 1. collect the positions of every view query
     std::vector<std::vector<uint32_t>> qpos(desc->n_queries);
-    uint32_t max_len = 0;
+    std::vector<uint32_t> long_views;
+    uint32_t max_len = 0, longest = 0;
     for (uint32_t v = 0; v < desc->n_queries; ++v) {
         const uint32_t q = desc->query_ids ? desc->query_ids[v] : v;
         if (q >= ds->nq) return fail("fr_dev_plan_create: query id out of range");
@@ -706,11 +707,13 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
             pos.resize(ds->q_len[q]);
             for (uint32_t k = 0; k < ds->q_len[q]; ++k) pos[k] = ds->q_start[q] + k;
         }
-        max_len = std::max<uint32_t>(max_len, (uint32_t)pos.size());
+        if (pos.size() > (size_t)kMaxTile) {
+            long_views.push_back(v);  // ranked from HBM by long_queries.cu
+            longest = std::max<uint32_t>(longest, (uint32_t)pos.size());
+        } else {
+            max_len = std::max<uint32_t>(max_len, (uint32_t)pos.size());
+        }
     }
-    if (max_len > (uint32_t)kMaxTile)
-        return fail("a query has " + std::to_string(max_len) + " documents; this build ranks at most " +
-                    std::to_string(kMaxTile) + " per query");
     pl->max_len = max_len;
     int tb = 128;
     if (const char *env = getenv("FASTRANK_TB")) tb = atoi(env) >= 256 ? 256 : 128;  // tuning knob
@@ -726,6 +729,7 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
     };
     for (uint32_t v = 0; v < desc->n_queries; ++v) {
         const uint32_t len = (uint32_t)qpos[v].size();
+        if (len > (uint32_t)kMaxTile) continue;
         if (cur_docs + len > (uint32_t)tb && cur_docs > 0) close_tile();
         const uint32_t start = cur_docs;
         pq_local.push_back(start | (len << 16));
@@ -741,7 +745,7 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
     pl->nt = (uint32_t)tile_doc_off.size() - 1;
     pl->nq_plan = (uint32_t)pq_local.size();
     // 3. discount table with the host libm (evaluators.rs:269: log2(i + 2))
-    std::vector<double> lg2(std::max<uint32_t>(max_len, 1));
+    std::vector<double> lg2(std::max<uint32_t>(std::max(max_len, longest), 1));
     for (size_t i = 0; i < lg2.size(); ++i) lg2[i] = std::log2((double)i + 2.0);
     cudaStream_t s = ds->stream;
     CU(pl->lg2.upload(lg2, s));
@@ -771,6 +775,11 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
         CU(cudaGetLastError());
     }
     if (build_fast_plan(pl.get(), tile_q_off, pq_local, pq_doc0, pd_pos)) return 1;
+    if (build_long_plan(pl.get(), qpos, long_views, desc)) return 1;
+    if (!long_views.empty()) {
+        pl->fast.ok = false;
+        pl->fast.why = "a query has more than 1024 documents";
+    }
     CU(cudaStreamSynchronize(s));
     pl->nq_global = pl->nq_view;
     *out = pl.release();
@@ -831,6 +840,13 @@ int fr_dev_eval_linear_batch(fr_dev_plan *pl, const double *w, size_t wlen, size
         a.err = pl->err_dev.p;
         if (pl->nt > 0 && launch_batch(pl, kc, pl->tb, a, s)) return 1;
     }
+    if (pl->lng.n_long > 0) {
+        std::vector<uint32_t> out_index(n_cand);
+        for (size_t c = 0; c < n_cand; ++c) out_index[c] = (uint32_t)c;
+        if (eval_long_linear(pl, w, wlen, n_cand, out_index.data(), pl->sums_dev.p,
+                             out_per_query ? pl->perq_dev.p : nullptr, pl->err_dev.p, s))
+            return 1;
+    }
     if (allreduce_sums(pl, pl->sums_dev.p, n_cand, s)) return 1;
     CU(cudaMemcpyAsync(pl->sums_host.p, pl->sums_dev.p, sizeof(long long) * n_cand,
                        cudaMemcpyDeviceToHost, s));
@@ -885,6 +901,21 @@ int fr_dev_eval_coord_sweeps(fr_dev_plan *pl, size_t n_sweeps, const double *bas
         a.cand_off = c0;
         a.err = pl->err_dev.p;
         if (pl->nt > 0 && launch_sweep(pl, kc, pl->tb, (uint32_t)n_sweeps, a, s)) return 1;
+    }
+    if (pl->lng.n_long > 0) {  // lists beyond the largest tile: every candidate as a full weight vector
+        std::vector<double> full;
+        std::vector<uint32_t> out_index;
+        for (size_t r = 0; r < n_sweeps; ++r) {
+            for (uint32_t k = 0; k < n_cand[r]; ++k) {
+                full.insert(full.end(), base_w + r * wlen, base_w + (r + 1) * wlen);
+                if (fid[r] < wlen) full[full.size() - wlen + fid[r]] = cand_w[r * cand_stride + k];
+                out_index.push_back((uint32_t)(r * cand_stride + k));
+            }
+        }
+        if (eval_long_linear(pl, full.data(), wlen, out_index.size(), out_index.data(), pl->sums_dev.p, nullptr,
+                             pl->err_dev.p, s))
+            return 1;
+        CU(cudaStreamSynchronize(s));  // `full` is staged from pageable memory
     }
     if (allreduce_sums(pl, pl->sums_dev.p, total, s)) return 1;
     CU(cudaMemcpyAsync(pl->sums_host.p, pl->sums_dev.p, sizeof(long long) * total,
@@ -962,6 +993,9 @@ int fr_dev_eval_model(fr_dev_plan *pl, const fr_dev_model *m, int64_t *out_sum_f
     if (pl->nt > 0 &&
         launch_scores_eval(pl, ds->scores_pos.p, pl->sums_dev.p, out_per_query ? pl->perq_dev.p : nullptr,
                            pl->err_dev.p, s))
+        return 1;
+    if (eval_long_scores(pl, ds->scores_pos.p, pl->sums_dev.p, out_per_query ? pl->perq_dev.p : nullptr,
+                         pl->err_dev.p, s))
         return 1;
     if (allreduce_sums(pl, pl->sums_dev.p, 1, s)) return 1;
     CU(cudaMemcpyAsync(pl->sums_host.p, pl->sums_dev.p, sizeof(long long), cudaMemcpyDeviceToHost, s));

@@ -260,9 +260,17 @@ struct FastView {
     uint32_t n_cls;
 };
 
+// Queries longer than the largest tile (long_queries.cu).
+struct LongPlan {
+    uint32_t n_long = 0, n_docs = 0;
+    DevBuf<uint32_t> lq_off, ld_pos, lq_view, out_idx;
+    DevBuf<double> lq_norm, scores, slots, w;
+};
+
 struct fr_dev_plan {
     fr_dev_dataset *ds = nullptr;
     FastPlan fast;
+    LongPlan lng;
     int metric = 0;
     int depth = INT_MAX;
     int tb = 128;
@@ -310,6 +318,14 @@ namespace frbdev {
 // defined in device.cu
 int check_err_flags(int flags);
 int allreduce_sums(fr_dev_plan *pl, long long *dev, size_t count, cudaStream_t stream);
+// defined in long_queries.cu
+int build_long_plan(fr_dev_plan *pl, const std::vector<std::vector<uint32_t>> &qpos,
+                    const std::vector<uint32_t> &long_views, const fr_dev_plan_desc *desc);
+int eval_long_linear(fr_dev_plan *pl, const double *w_host, size_t wlen, size_t n_vec,
+                     const uint32_t *out_index, long long *sums_dev, double *perq_dev, int *err_dev,
+                     cudaStream_t s);
+int eval_long_scores(fr_dev_plan *pl, const double *scores_pos, long long *sums_dev, double *perq_dev,
+                     int *err_dev, cudaStream_t s);
 // defined in trees.cu
 int build_forest(fr_dev_model *m, const uint64_t *code, size_t n_words);
 int launch_forest(fr_dev_dataset *ds, const fr_dev_model *m, double *out_pos, double *out_inst,

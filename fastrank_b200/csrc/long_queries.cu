@@ -1,0 +1,231 @@
+// long_queries.cu -- queries longer than the largest tile (1024 documents).
+//
+// The tile kernels rank a whole query inside one CTA's shared memory; a query that does not fit
+// (MSLR-WEB30K has lists of ~1.2k documents, the reference sorts lists of any length,
+// evaluators.rs:206-221) takes this path instead: scores go to a scratch array in HBM, one CTA
+// per (query, candidate) ranks by counting straight from L2, metric terms are scattered to their
+// rank and folded in rank order by one thread -- the same arithmetic, in the same order, as
+// rank_and_metric in device.cu, so results are bit-identical to the oracle here too.  It is a
+// correctness path (O(len^2) global loads per list), not a tuned one: long lists are rare.
+#include "device_common.cuh"
+
+namespace {
+
+constexpr double kFxLong = 1099511627776.0;
+static_assert(FR_FX_BITS == 40, "kFxLong must match FR_FX_BITS");
+constexpr int kLongChunk = 16;  // candidates per pass (bounds the scratch arrays)
+
+struct LongView {
+    const uint32_t *lq_off;   // n_long + 1, into ld_pos
+    const uint32_t *ld_pos;   // position of every document of the long queries
+    const uint32_t *lq_view;  // view (output) index of the query
+    const double *lq_norm;    // ideal DCG (NaN = none) or num_relevant
+    uint32_t n_docs;
+};
+
+// dense_dataset.rs:67-76 for documents of long queries: scores[k][d], left-to-right f64 dot
+__global__ void long_linear_scores_kernel(const float *__restrict__ x, size_t ld, uint32_t dm,
+                                          LongView L, const double *__restrict__ w, uint32_t wlen,
+                                          double *__restrict__ scores) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= L.n_docs) return;
+    const float *__restrict__ xp = x + L.ld_pos[d];
+    const double *__restrict__ wk = w + (size_t)blockIdx.y * wlen;
+    double acc = 0.0;
+    for (uint32_t j = 0; j < dm; ++j)
+        acc = __dadd_rn(acc, __dmul_rn((double)__ldg(xp + (size_t)j * ld), __ldg(wk + j)));
+    scores[(size_t)blockIdx.y * L.n_docs + d] = acc;
+}
+
+__global__ void long_gather_scores_kernel(LongView L, const double *__restrict__ scores_pos,
+                                          double *__restrict__ scores) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < L.n_docs) scores[d] = scores_pos[L.ld_pos[d]];
+}
+
+__device__ __forceinline__ unsigned long long long_key(double s) {
+    long long b = __double_as_longlong(s);
+    if ((b << 1) == 0) b = 0;  // -0.0 == +0.0 (evaluators.rs:36)
+    const unsigned long long u = (unsigned long long)b;
+    return b < 0 ? ~u : (u | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(256) long_rank_kernel(PlanView P, LongView L, const double *__restrict__ scores,
+                                                        double *__restrict__ slots,
+                                                        const uint32_t *__restrict__ out_idx, long long *sums,
+                                                        double *perq, int *err) {
+    const uint32_t q = blockIdx.x, k = blockIdx.y;
+    const uint32_t base = L.lq_off[q], len = L.lq_off[q + 1] - base;
+    const double *__restrict__ sc = scores + (size_t)k * L.n_docs + base;
+    double *sl = slots + (size_t)k * L.n_docs + base;
+    for (uint32_t t = threadIdx.x; t < len; t += blockDim.x) {
+        const double st = sc[t];
+        if (st != st) atomicOr(err, ERR_NAN_SCORE);
+        const unsigned long long kt = long_key(st);
+        uint32_t cnt = 0;
+        for (uint32_t j = 0; j < len; ++j) {
+            const unsigned long long kj = long_key(__ldg(sc + j));
+            cnt += (kj > kt) | ((kj == kt) & (j < t));
+        }
+        const uint32_t pos = L.ld_pos[base + t];
+        double payload;
+        if (P.metric == FR_METRIC_NDCG) {
+            const double ge = P.gexp[pos];
+            payload = ((int)cnt < P.depth && ge != 0.0) ? ge / P.lg2[cnt] : 0.0;  // evaluators.rs:265-270
+        } else {
+            payload = P.gain[pos] > 0.0f ? 1.0 : 0.0;
+        }
+        sl[cnt] = payload;
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const double norm = L.lq_norm[q];
+    double value = 0.0;
+    if (P.metric == FR_METRIC_NDCG) {
+        if (norm == norm) {
+            const uint32_t lim = len < (uint32_t)P.depth ? len : (uint32_t)P.depth;
+            double dcg = 0.0;
+            for (uint32_t r = 0; r < lim; ++r) dcg = __dadd_rn(dcg, sl[r]);
+            if (dcg > norm) atomicOr(err, ERR_DCG_ABOVE_IDEAL);
+            value = dcg / norm;
+        }
+    } else if (P.metric == FR_METRIC_AP) {
+        if (norm > 0.0) {
+            unsigned recall = 0;
+            double sum = 0.0;
+            for (uint32_t r = 0; r < len; ++r) {
+                if (sl[r] != 0.0) {
+                    recall += 1;
+                    sum = __dadd_rn(sum, (double)recall / (double)(r + 1));
+                }
+            }
+            value = sum / norm;
+        }
+    } else {
+        for (uint32_t r = 0; r < len; ++r) {
+            if (sl[r] != 0.0) {
+                value = 1.0 / (double)(r + 1);
+                break;
+            }
+        }
+    }
+    const uint32_t o = out_idx[k];
+    if (perq) perq[(size_t)o * P.nq_view + L.lq_view[q]] = value;
+    atomicAdd((unsigned long long *)(sums + o), (unsigned long long)__double2ll_rn(value * kFxLong));
+}
+
+LongView long_view(const fr_dev_plan *pl) {
+    LongView v;
+    v.lq_off = pl->lng.lq_off.p;
+    v.ld_pos = pl->lng.ld_pos.p;
+    v.lq_view = pl->lng.lq_view.p;
+    v.lq_norm = pl->lng.lq_norm.p;
+    v.n_docs = pl->lng.n_docs;
+    return v;
+}
+
+int rank_chunk(fr_dev_plan *pl, uint32_t n_chunk, const uint32_t *out_idx_dev, long long *sums_dev,
+               double *perq_dev, int *err_dev, cudaStream_t s) {
+    LongPlan &lp = pl->lng;
+    long_rank_kernel<<<dim3(lp.n_long, n_chunk), 256, 0, s>>>(pl->view(), long_view(pl), lp.scores.p, lp.slots.p,
+                                                             out_idx_dev, sums_dev, perq_dev, err_dev);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+namespace frbdev {
+
+// Host half: the lists that did not fit a tile, their norms (plan_norms_kernel's arithmetic
+// restated with the host's libm-built tables) and the scratch arrays.
+int build_long_plan(fr_dev_plan *pl, const std::vector<std::vector<uint32_t>> &qpos,
+                    const std::vector<uint32_t> &long_views, const fr_dev_plan_desc *desc) {
+    LongPlan &lp = pl->lng;
+    fr_dev_dataset *ds = pl->ds;
+    lp.n_long = (uint32_t)long_views.size();
+    lp.n_docs = 0;
+    if (lp.n_long == 0) return 0;
+    std::vector<uint32_t> lq_off{0}, ld_pos, lq_view;
+    std::vector<double> lq_norm;
+    for (uint32_t v : long_views) {
+        const std::vector<uint32_t> &pos = qpos[v];
+        const uint32_t len = (uint32_t)pos.size();
+        const bool has_ov = desc->norm_present && desc->norm_value && desc->norm_present[v] != 0;
+        double norm = 0.0;
+        if (pl->metric == FR_METRIC_NDCG) {
+            if (has_ov) {
+                norm = desc->norm_value[v];
+            } else if (!(ds->gain_pos[pos[len - 1]] > 0.0f)) {  // positions are gain-ascending
+                norm = std::nan("");
+            } else {
+                const uint32_t lim = len < (uint32_t)pl->depth ? len : (uint32_t)pl->depth;
+                double dcg = 0.0;
+                for (uint32_t i = 0; i < lim; ++i) {
+                    const double ge = std::pow(2.0, (double)ds->gain_pos[pos[len - 1 - i]]) - 1.0;
+                    dcg += ge / std::log2((double)i + 2.0);
+                }
+                norm = dcg;
+            }
+        } else if (pl->metric == FR_METRIC_AP) {
+            uint32_t rel = 0;
+            for (uint32_t p : pos) rel += ds->gain_pos[p] > 0.0f;
+            norm = (has_ov && desc->norm_value[v] > 0.0) ? desc->norm_value[v] : (double)rel;
+        }
+        ld_pos.insert(ld_pos.end(), pos.begin(), pos.end());
+        lq_off.push_back((uint32_t)ld_pos.size());
+        lq_view.push_back(v);
+        lq_norm.push_back(norm);
+    }
+    lp.n_docs = (uint32_t)ld_pos.size();
+    cudaStream_t s = ds->stream;
+    CU(lp.lq_off.upload(lq_off, s));
+    CU(lp.ld_pos.upload(ld_pos, s));
+    CU(lp.lq_view.upload(lq_view, s));
+    CU(lp.lq_norm.upload(lq_norm, s));
+    CU(lp.scores.alloc((size_t)kLongChunk * lp.n_docs));
+    CU(lp.slots.alloc((size_t)kLongChunk * lp.n_docs));
+    CU(lp.out_idx.alloc(kLongChunk));
+    CU(lp.w.alloc(1));
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// n_vec full weight vectors (host, row-major n_vec x wlen); vector i adds into sums[out_index[i]]
+int eval_long_linear(fr_dev_plan *pl, const double *w_host, size_t wlen, size_t n_vec,
+                     const uint32_t *out_index, long long *sums_dev, double *perq_dev, int *err_dev,
+                     cudaStream_t s) {
+    LongPlan &lp = pl->lng;
+    if (lp.n_long == 0 || n_vec == 0) return 0;
+    fr_dev_dataset *ds = pl->ds;
+    const uint32_t dm = (uint32_t)std::min<size_t>(wlen, ds->d);
+    CU(lp.w.ensure((size_t)kLongChunk * std::max<size_t>(wlen, 1)));
+    for (size_t c0 = 0; c0 < n_vec; c0 += kLongChunk) {
+        const uint32_t nc = (uint32_t)std::min<size_t>(kLongChunk, n_vec - c0);
+        CU(cudaMemcpyAsync(lp.w.p, w_host + c0 * wlen, sizeof(double) * nc * wlen, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(lp.out_idx.p, out_index + c0, sizeof(uint32_t) * nc, cudaMemcpyHostToDevice, s));
+        long_linear_scores_kernel<<<dim3((lp.n_docs + 127) / 128, nc), 128, 0, s>>>(
+            ds->x.p, ds->ld, dm, long_view(pl), lp.w.p, (uint32_t)wlen, lp.scores.p);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        if (rank_chunk(pl, nc, lp.out_idx.p, sums_dev, perq_dev, err_dev, s)) return 1;
+    }
+    return 0;
+}
+
+// scores already in HBM by position (trees, ensembles); adds into sums[0]
+int eval_long_scores(fr_dev_plan *pl, const double *scores_pos, long long *sums_dev, double *perq_dev,
+                     int *err_dev, cudaStream_t s) {
+    LongPlan &lp = pl->lng;
+    if (lp.n_long == 0) return 0;
+    const uint32_t zero = 0;
+    CU(cudaMemcpyAsync(lp.out_idx.p, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    long_gather_scores_kernel<<<(lp.n_docs + 127) / 128, 128, 0, s>>>(long_view(pl), scores_pos, lp.scores.p);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return rank_chunk(pl, 1, lp.out_idx.p, sums_dev, perq_dev, err_dev, s);
+}
+
+}  // namespace frbdev

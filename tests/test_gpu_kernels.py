@@ -198,3 +198,67 @@ def test_fixed_point_sum_is_geometry_independent(oracle):
         assert a.tolist() == b.tolist()
     finally:
         dev.close()
+
+
+def test_lists_longer_than_the_largest_tile(oracle):
+    """Queries of 1025 .. 3000 documents (MSLR-sized lists and beyond) are ranked from HBM by
+    long_queries.cu; everything stays bit-identical to the oracle, next to ordinary queries."""
+    rng = np.random.default_rng(21)
+    lens = [5, 1025, 40, 1500, 1024, 3000, 17]
+    qid = np.concatenate([np.full(l, 7 + i) for i, l in enumerate(lens)]).astype(np.int64)
+    n = len(qid)
+    X = rng.normal(size=(n, 6)).astype(np.float32)
+    X[:, 2] = rng.integers(0, 4, n)          # ties
+    y = rng.integers(0, 5, n).astype(np.float64)
+    ods = oracle_dataset(oracle, X, y, qid)
+    qidx, nq = dense_qidx(qid)
+    dev = DevDataset(X, y.astype(np.float32), qidx, nq)
+    W = rng.normal(size=(19, 6))             # more candidates than one scratch chunk
+    W[1, :] = 0.0
+    W[1, 2] = 1.0
+    try:
+        for name, metric, depth in METRICS:
+            plan = dev.plan(metric, depth)
+            assert dev.lib.fr_dev_plan_has_fast_sweep(plan.ptr) == 0
+            sums, pq = plan.eval_linear(W)
+            for c in range(W.shape[0]):
+                exp = oracle.evaluate_scores(ods, oracle.score_linear(X, W[c]), name)
+                assert np.array_equal(pq[c], exp), (name, c)
+                assert int(sums[c]) == fx_sum(exp)
+        plan = dev.plan(0, 10)
+        base = rng.normal(size=(2, 6))
+        cands = [[0.0, 0.3, -1.0], [base[1, 5], 2.0]]
+        sums = plan.coord_sweeps(base, [2, 5], cands)
+        for r, f in enumerate([2, 5]):
+            for k, wv in enumerate(cands[r]):
+                w = base[r].copy()
+                w[f] = wv
+                assert int(sums[r, k]) == fx_sum(oracle.evaluate_scores(ods, oracle.score_linear(X, w), "ndcg@10"))
+    finally:
+        dev.close()
+
+
+def test_long_lists_through_the_api(oracle):
+    import fastrank_b200 as fr
+
+    rng = np.random.default_rng(22)
+    lens = [1300, 30, 2100, 64]
+    qid = np.concatenate([np.full(l, i) for i, l in enumerate(lens)]).astype(np.int64)
+    n = len(qid)
+    X = rng.normal(size=(n, 5)).astype(np.float32)
+    y = (rng.random(n) < 0.2).astype(np.float64) * rng.integers(1, 4, n)
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    ods = oracle_dataset(oracle, X, y, qid)
+    tree = {"FeatureSplit": {"fid": 1, "split": 0.1, "lhs": {"LeafNode": 1.0},
+                             "rhs": {"FeatureSplit": {"fid": 3, "split": -0.2, "lhs": {"LeafNode": 0.5}, "rhs": {"LeafNode": 2.0}}}}}
+    for spec in ({"Linear": {"weights": [0.2, -1.0, 0.5, 0.0, 3.0]}}, {"DecisionTree": tree}):
+        m = fr.CModel.from_dict(spec)
+        for measure in ("ndcg@10", "map", "rr"):
+            assert ds.evaluate(m, measure) == oracle.evaluate_model(ods, spec, measure)
+    req = fr.TrainRequest.coordinate_ascent()
+    req.measure = "ndcg@10"
+    req.params.num_restarts, req.params.seed, req.params.quiet = 2, 5, True
+    model = ds.train_model(req)  # long lists: the exact-order sweep serves the line searches
+    w = model.to_dict()["Linear"]["weights"]
+    exp = oracle.mean(oracle.evaluate_scores(ods, oracle.score_linear(X, w), "ndcg@10"))
+    assert ds.evaluate_mean(model, "ndcg@10") == pytest.approx(exp, abs=1e-12)
