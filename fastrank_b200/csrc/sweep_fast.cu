@@ -405,9 +405,22 @@ int launch_fast(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStrea
     const uint32_t dm8 = (a.dm + 7) & ~7u;
     const SmemLayout L(TB, (int)sizeof(typename SlotType<TB>::type), WS ? dm8 * kMaxSweeps : 0u);
     auto kernel = sweep_fast_kernel<TB, TD, WS>;
-    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    // attribute + occupancy queries cost several microseconds each: once per (instantiation,
+    // device, shared-memory size), not once per launch
+    static std::mutex mu;
+    static std::map<std::pair<int, size_t>, int> cache;
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TB, L.total));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        const auto key = std::make_pair(pl->ds->device, L.total);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TB, L.total));
+            it = cache.emplace(key, occ).first;
+        }
+        occ = it->second;
+    }
     if (occ < 1) return fail("sweep_fast_kernel does not fit on an SM");
     uint64_t total = (uint64_t)pl->sm_count * (uint64_t)occ;
     uint32_t gx = (uint32_t)std::max<uint64_t>(1, total / n_groups);

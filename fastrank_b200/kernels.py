@@ -158,6 +158,29 @@ class DevPlan:
         self.ds._check(rc)
         return sums
 
+    def pack_sweeps(self, base_w: np.ndarray, fids, cands):
+        """Builds the flat arrays fr_dev_eval_coord_sweeps[_fast] takes (done once, outside any
+        timed region, by callers that replay the same sweeps)."""
+        base_w = np.ascontiguousarray(base_w, dtype=np.float64)
+        r = base_w.shape[0]
+        stride = max(len(c) for c in cands)
+        cw = np.zeros((r, stride), dtype=np.float64)
+        nc = np.zeros(r, dtype=np.uint32)
+        for i, c in enumerate(cands):
+            cw[i, : len(c)] = c
+            nc[i] = len(c)
+        return base_w, np.ascontiguousarray(fids, dtype=np.uint32), cw, nc, np.zeros((r, stride), dtype=np.int64)
+
+    def coord_sweeps_packed(self, packed, fast: bool = True):
+        ffi, lib = self.ds.ffi, self.ds.lib
+        base_w, fid, cw, nc, sums = packed
+        args = (self.ptr, base_w.shape[0], ffi.cast("double*", base_w.ctypes.data), base_w.shape[1],
+                ffi.cast("uint32_t*", fid.ctypes.data), ffi.cast("double*", cw.ctypes.data),
+                ffi.cast("uint32_t*", nc.ctypes.data), cw.shape[1], ffi.cast("int64_t*", sums.ctypes.data))
+        rc = lib.fr_dev_eval_coord_sweeps_fast(*args, ffi.NULL) if fast else lib.fr_dev_eval_coord_sweeps(*args)
+        self.ds._check(rc)
+        return sums
+
     def close(self):
         if self.ptr is not None:
             self.ds.lib.fr_dev_plan_destroy(self.ptr)
