@@ -35,7 +35,7 @@
 namespace {
 
 constexpr int kMaxSweeps = 8;  // sweeps sharing one pass over X (one blockIdx.y group)
-constexpr int kMaxRows = kMaxSweeps * 32;
+constexpr int kMaxRows = kMaxSweeps * 64;  // 8 sweeps x (1 + 2 x 25) candidates fit one pass
 constexpr int kSmemTbl = 64;   // discount-table entries kept in shared memory
 constexpr double kFx = 1099511627776.0;
 static_assert(FR_FX_BITS == 40, "kFx must match FR_FX_BITS");
@@ -640,7 +640,7 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         a.tile_ctr = ctr_dev;
         if (pl->nt == 0) continue;
         // the weight table is staged in shared memory while that costs no resident CTA
-        bool ws = (size_t)((a.dm + 7) & ~7u) * kMaxSweeps * sizeof(double) <= 10 * 1024;
+        bool ws = SmemLayout(128, 1, ((a.dm + 7) & ~7u) * kMaxSweeps).total <= 56 * 1024;
         if (const char *env = getenv("FASTRANK_WSMEM")) ws = atoi(env) != 0;
         int rc;
         if (pl->tb == 128) {
