@@ -527,6 +527,13 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
                 i += n;
             }
         }
+        // longest task first: the tile's warps pull tasks from a shared queue, and the phase ends
+        // at a barrier, so the long walks must not be the ones left for last
+        std::stable_sort(tasks.begin() + tile_task_off.back(), tasks.end(), [](const uint2 &a, const uint2 &b) {
+            const uint32_t ca = ((a.x >> 16) - (a.x & 0xffffu)) * (8 + (a.y >> 16));
+            const uint32_t cb = ((b.x >> 16) - (b.x & 0xffffu)) * (8 + (b.y >> 16));
+            return ca > cb;
+        });
         tile_task_off.push_back((uint32_t)tasks.size());
     }
     fp.n_tasks = (uint32_t)tasks.size();
