@@ -108,6 +108,58 @@ struct SmemLayout {
 // misc words
 enum { M_F = 0, M_TILE = 16, M_NEXT = 17, M_CTR = 18, M_SWROW = 20 /* 9 entries */ };
 
+// One warp task: rank W documents [t0, t0 + n) of the query occupying tile-local [qs, qe)
+// under the 32 candidate rows of the lanes (myrow = this lane's row of the score matrix).
+template <int W, typename slot_t>
+__device__ __forceinline__ void rank_task(const double *__restrict__ myrow, int qs, int qe, int t0, int n,
+                                          unsigned lim, bool live, bool tag_cls,
+                                          const uint8_t *__restrict__ s_cls, slot_t *__restrict__ slots,
+                                          int lane) {
+    double st[W];
+    unsigned cnt[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const int tt = t0 + i < qe ? t0 + i : qe - 1;
+        st[i] = myrow[tt];
+        cnt[i] = 0;
+    }
+    int jq = qs;
+#pragma unroll 4
+    for (; jq < t0; ++jq) {  // documents that win ties against the task's
+        const double sj = myrow[jq];
+#pragma unroll
+        for (int i = 0; i < W; ++i) count_ge(cnt[i], sj, st[i]);
+    }
+#pragma unroll
+    for (int jj = 0; jj < W; ++jj) {
+        if (jj < n) {
+            const double sj = myrow[t0 + jj];
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                if (i < jj) count_gt(cnt[i], sj, st[i]);
+                if (i > jj) count_ge(cnt[i], sj, st[i]);
+            }
+        }
+    }
+    jq = t0 + n;
+#pragma unroll 4
+    for (; jq < qe; ++jq) {  // documents that lose ties
+        const double sj = myrow[jq];
+#pragma unroll
+        for (int i = 0; i < W; ++i) count_gt(cnt[i], sj, st[i]);
+    }
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            if (i < n && cnt[i] < lim) {
+                // what the fold needs: the gain class (table), else the document
+                const unsigned tag = tag_cls ? (unsigned)s_cls[t0 + i] + 1u : (unsigned)(t0 + i + 1);
+                slots[(size_t)(qs + cnt[i]) * 32 + lane] = (slot_t)tag;
+            }
+        }
+    }
+}
+
 template <int TB, int TD, bool WS>
 __global__ void __launch_bounds__(TB, (TB == 128 ? (WS ? 4 : 5) : 2))
 sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
@@ -276,54 +328,16 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
                     const uint2 tk = s_tasks[ti];
                     const int qs = (int)(tk.x & 0xffffu), qe = (int)(tk.x >> 16);
                     const int t0 = (int)(tk.y & 0xffffu), n = (int)(tk.y >> 16);
-                    double st[TD];
-                    unsigned cnt[TD];
-#pragma unroll
-                    for (int i = 0; i < TD; ++i) {
-                        const int tt = t0 + i < qe ? t0 + i : qe - 1;
-                        st[i] = myrow[tt];
-                        cnt[i] = 0;
-                    }
-                    int jq = qs;
-#pragma unroll 4
-                    for (; jq < t0; ++jq) {  // documents that win ties against the task's
-                        const double sj = myrow[jq];
-#pragma unroll
-                        for (int i = 0; i < TD; ++i) count_ge(cnt[i], sj, st[i]);
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < TD; ++jj) {
-                        if (jj < n) {
-                            const double sj = myrow[t0 + jj];
-#pragma unroll
-                            for (int i = 0; i < TD; ++i) {
-                                if (i < jj) count_gt(cnt[i], sj, st[i]);
-                                if (i > jj) count_ge(cnt[i], sj, st[i]);
-                            }
-                        }
-                    }
-                    jq = t0 + n;
-#pragma unroll 4
-                    for (; jq < qe; ++jq) {  // documents that lose ties
-                        const double sj = myrow[jq];
-#pragma unroll
-                        for (int i = 0; i < TD; ++i) count_gt(cnt[i], sj, st[i]);
-                    }
-                    if (lane < nrow) {
-                        const unsigned len = (unsigned)(qe - qs);
-                        const unsigned lim =
-                            (P.metric == FR_METRIC_NDCG && (unsigned)P.depth < len) ? (unsigned)P.depth : len;
-#pragma unroll
-                        for (int i = 0; i < TD; ++i) {
-                            if (i < n && cnt[i] < lim) {
-                                // what the fold needs: the gain class (table), else the document
-                                const unsigned tag = (P.metric == FR_METRIC_NDCG && use_tbl)
-                                                         ? (unsigned)s_cls[t0 + i] + 1u
-                                                         : (unsigned)(t0 + i + 1);
-                                slots[(size_t)(qs + cnt[i]) * 32 + lane] = (slot_t)tag;
-                            }
-                        }
-                    }
+                    const unsigned len = (unsigned)(qe - qs);
+                    const unsigned lim =
+                        (P.metric == FR_METRIC_NDCG && (unsigned)P.depth < len) ? (unsigned)P.depth : len;
+                    const bool tag_cls = P.metric == FR_METRIC_NDCG && use_tbl;
+                    // a short last chunk of a query takes the half-width walk
+                    if (TD > 4 && n <= TD / 2)
+                        rank_task<(TD > 4 ? TD / 2 : TD), slot_t>(myrow, qs, qe, t0, n, lim, lane < nrow, tag_cls, s_cls,
+                                                                  slots, lane);
+                    else
+                        rank_task<TD, slot_t>(myrow, qs, qe, t0, n, lim, lane < nrow, tag_cls, s_cls, slots, lane);
                     ti = __shfl_sync(0xffffffffu, tnext, 0);
                 }
             }
