@@ -540,6 +540,8 @@ int launch_scores_eval(fr_dev_plan *pl, const double *scores, long long *sums, d
 namespace frbdev {
 int check_err_flags(int flags) {
     if (flags & ERR_NAN_SCORE) return fail("Model.predict -> NaN (a score was NaN)");
+    if (flags & ERR_PEER_TIMEOUT)
+        return fail("timed out waiting for a peer GPU's metric sums (did every rank make the same call?)");
     if (flags & ERR_DCG_ABOVE_IDEAL)
         return fail("actual DCG exceeds ideal DCG for some query (inconsistent judgments)");
     return 0;
@@ -1078,6 +1080,49 @@ int fr_dev_comm_create(int device, int rank, int world, const uint8_t id[128], f
     if (rc != 0)
         return fail(std::string("ncclCommInitRank: ") + (api.GetErrorString ? api.GetErrorString(rc) : "?"));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (world > 1 && !(getenv("FASTRANK_P2P") && atoi(getenv("FASTRANK_P2P")) == 0) && api.AllGather) {
+        // Mailboxes for the fused reduction: allocate, exchange IPC handles with an all-gather,
+        // map every peer.  Any failure anywhere leaves every rank on the NCCL all-reduce.
+        Mailbox &mb = c->mail;
+        int good = 1;
+        DevBuf<unsigned char> handles;
+        std::vector<cudaIpcMemHandle_t> all(world);
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof(mine));
+        if (mb.mem.alloc(Mailbox::bytes(world)) != cudaSuccess ||
+            cudaMemset(mb.mem.p, 0, Mailbox::bytes(world)) != cudaSuccess ||
+            cudaIpcGetMemHandle(&mine, mb.mem.p) != cudaSuccess)
+            good = 0;
+        CU(handles.alloc(sizeof(cudaIpcMemHandle_t) * (size_t)(world + 1)));
+        CU(cudaMemcpy(handles.p + sizeof(mine) * world, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+        if (api.AllGather(handles.p + sizeof(mine) * world, handles.p, sizeof(mine), kNcclUint8, c->comm, c->stream) != 0)
+            return fail("ncclAllGather of the mailbox handles failed");
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(all.data(), handles.p, sizeof(mine) * world, cudaMemcpyDeviceToHost));
+        mb.peer.assign(world, nullptr);
+        for (int r = 0; r < world && good; ++r) {
+            if (r == rank) {
+                mb.peer[r] = mb.mem.p;
+                continue;
+            }
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                good = 0;
+                break;
+            }
+            mb.opened.push_back(ptr);
+            mb.peer[r] = (unsigned char *)ptr;
+        }
+        cudaGetLastError();
+        uint64_t agree = good ? 0 : 1;  // sum of failures over all ranks
+        if (fr_dev_comm_allreduce_u64(c.get(), &agree, 1)) return 1;
+        if (agree == 0) {
+            std::vector<unsigned char *> hp(mb.peer);
+            CU(mb.peer_dev.upload(hp));
+            CU(cudaDeviceSynchronize());
+            mb.ok = true;
+        }
+    }
     *out = c.release();
     return 0;
 }
@@ -1085,6 +1130,7 @@ int fr_dev_comm_create(int device, int rank, int world, const uint8_t id[128], f
 void fr_dev_comm_destroy(fr_dev_comm *comm) {
     if (!comm) return;
     cudaSetDevice(comm->device);
+    for (void *ptr : comm->mail.opened) cudaIpcCloseMemHandle(ptr);
     if (comm->comm && nccl().ok) nccl().CommDestroy(comm->comm);
     if (comm->stream) cudaStreamDestroy(comm->stream);
     delete comm;

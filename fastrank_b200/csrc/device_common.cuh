@@ -96,6 +96,7 @@ struct NcclApi {
     int (*GetUniqueId)(UniqueId *) = nullptr;
     int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
     int (*CommDestroy)(void *) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool ok = false;
@@ -125,6 +126,7 @@ inline NcclApi &nccl() {
             (int (*)(void **, int, NcclApi::UniqueId, int))dlsym(h, "ncclCommInitRank");
         api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *,
                                  cudaStream_t))dlsym(h, "ncclAllReduce");
+        api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(h, "ncclAllGather");
         api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
         api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
         api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
@@ -132,15 +134,33 @@ inline NcclApi &nccl() {
     });
     return api;
 }
+constexpr int kNcclUint8 = 1;
 constexpr int kNcclInt64 = 4;
 constexpr int kNcclUint64 = 5;
 constexpr int kNcclSum = 0;
 
 constexpr int ERR_NAN_SCORE = 1;
 constexpr int ERR_DCG_ABOVE_IDEAL = 2;
+constexpr int ERR_PEER_TIMEOUT = 4;
 
 }  // namespace frbdev
 using namespace frbdev;
+
+// Peer-memory mailboxes for the sweep kernel's fused reduction (sweep_fast.cu): every rank maps
+// every other rank's mailbox through CUDA IPC (NVLink / NVSwitch peer stores).
+//   mailbox = 2 epochs x world slots x kMailWords int64, then 2 x world u32 arrival flags
+constexpr uint32_t kMailWords = 4096;
+struct Mailbox {
+    bool ok = false;
+    DevBuf<unsigned char> mem;            // this rank's mailbox
+    std::vector<unsigned char *> peer;    // peer[r]: rank r's mailbox as seen from this device
+    std::vector<void *> opened;           // IPC mappings to close
+    DevBuf<unsigned char *> peer_dev;     // the same pointers, for the kernel
+    uint32_t epoch = 0;                   // one per fused reduction, identical on every rank
+    __host__ __device__ static size_t slot_bytes() { return sizeof(long long) * kMailWords; }
+    __host__ __device__ static size_t flags_offset(int world) { return 2 * (size_t)world * slot_bytes(); }
+    static size_t bytes(int world) { return flags_offset(world) + 2 * (size_t)world * sizeof(uint32_t); }
+};
 
 struct fr_dev_comm {
     int device = 0;
@@ -149,6 +169,7 @@ struct fr_dev_comm {
     void *comm = nullptr;
     cudaStream_t stream = nullptr;
     DevBuf<uint64_t> scratch;
+    Mailbox mail;
 };
 
 struct fr_dev_dataset {

@@ -56,7 +56,21 @@ struct FastArgs {
     uint32_t dm;  // min(wlen, features): zip() truncation of dense_dataset.rs:67-76
     unsigned *tile_ctr;  // [n_groups] zeroed before the launch: tiles are handed out dynamically
     int *err;
+    // fused cross-GPU reduction (nullptr: single GPU, or the NCCL all-reduce follows the kernel)
+    unsigned char *const *mail_peers;  // [world] every rank's mailbox, own included
+    unsigned *done_ctr;                // CTAs that have flushed their sums (zeroed before the launch)
+    uint32_t mail_rank, mail_world, mail_epoch, mail_words;
 };
+
+// system-scope flag accesses for the peer mailboxes
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // cnt += (a >= b) / (a > b) as DSETP + predicated add (what nvcc emits for the C form is a
 // three-instruction add / compare / undo sequence).
@@ -222,8 +236,7 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     const double *myrow = s_score + (size_t)lane * ROW;
 
 
-    if (G == 0) return;
-    for (uint32_t tile = (uint32_t)s_misc[M_TILE]; tile < P.nt; tile = (uint32_t)s_misc[M_NEXT]) {
+    for (uint32_t tile = G > 0 ? (uint32_t)s_misc[M_TILE] : P.nt; tile < P.nt; tile = (uint32_t)s_misc[M_NEXT]) {
         // the next tile is claimed now; the value is read after this tile's last barrier
         if (t == 0) s_misc[M_NEXT] = (int)atomicAdd(A.tile_ctr + blockIdx.y, 1u);
         const uint32_t doc0 = P.tile_doc_off[tile];
@@ -412,6 +425,49 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     __syncthreads();
     for (int idx = t; idx < R; idx += TB)
         atomicAdd((unsigned long long *)(A.sums + A.row_out[row0 + idx]), s_sum[idx]);
+    if (A.mail_peers == nullptr) return;
+
+    // ---- fused all-reduce over peer memory ----
+    // The last CTA of this GPU to flush its sums stores the GPU's partial sums into every rank's
+    // mailbox (NVLink peer stores), raises its arrival flag there, waits for the flags of all
+    // ranks in its own mailbox and leaves the rank-ordered integer total in A.sums: the kernel
+    // that ranks is the kernel that reduces, no separate collective launch follows.
+    __threadfence();
+    __syncthreads();
+    if (t == 0) s_misc[M_TILE] = atomicAdd(A.done_ctr, 1u) == gridDim.x * gridDim.y - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_misc[M_TILE]) return;
+    __threadfence();
+    const uint32_t world = A.mail_world, me = A.mail_rank, buf = A.mail_epoch & 1u, nw = A.mail_words;
+    const size_t slot = sizeof(long long) * kMailWords;
+    for (uint32_t r = 0; r < world; ++r) {
+        long long *dst = (long long *)(A.mail_peers[r] + ((size_t)buf * world + me) * slot);
+        for (uint32_t i = t; i < nw; i += TB) dst[i] = __ldcg(A.sums + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((uint32_t)t < world) {
+        unsigned *flag = (unsigned *)(A.mail_peers[t] + Mailbox::flags_offset((int)world)) + buf * world + me;
+        st_release_sys(flag, A.mail_epoch);
+        const unsigned *mine = (const unsigned *)(A.mail_peers[me] + Mailbox::flags_offset((int)world)) + buf * world + t;
+        const long long t_begin = clock64();
+        while (ld_acquire_sys(mine) != A.mail_epoch) {
+            if (clock64() - t_begin > 8000000000ll) {  // ~4 s: a peer never made this call
+                atomicOr(A.err, ERR_PEER_TIMEOUT);
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    const unsigned char *box = A.mail_peers[me] + (size_t)buf * world * slot;
+    for (uint32_t i = t; i < nw; i += TB) {
+        long long total = 0;
+        for (uint32_t r = 0; r < world; ++r)
+            total += *(const volatile long long *)(box + (size_t)r * slot + sizeof(long long) * i);
+        A.sums[i] = total;
+    }
 }
 
 template <int TB, int TD, bool WS>
@@ -438,7 +494,7 @@ int launch_fast(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStrea
     if (occ < 1) return fail("sweep_fast_kernel does not fit on an SM");
     uint64_t total = (uint64_t)pl->sm_count * (uint64_t)occ;
     uint32_t gx = (uint32_t)std::max<uint64_t>(1, total / n_groups);
-    if (gx > pl->nt) gx = pl->nt;
+    if (gx > pl->nt) gx = std::max<uint32_t>(pl->nt, 1);  // an empty shard still takes part in the reduction
     PlanView pv = pl->view();
     FastView fv;
     fv.tile_task_off = pl->fast.tile_task_off.p;
@@ -591,7 +647,7 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
                             sizeof(uint32_t) * (n_sweeps + 2 * max_rows + n_groups + 1);
     // One device blob cleared with one memset and read back with one D2H copy:
     //   [sums i64 x total][err i32][pad i32][tile counters u32 x n_groups]
-    const size_t out_bytes = sizeof(long long) * total + 8 + sizeof(unsigned) * n_groups;
+    const size_t out_bytes = sizeof(long long) * total + 8 + sizeof(unsigned) * (n_groups + 1);
     CU(fp.in_dev.ensure(in_bytes));
     CU(fp.in_host.ensure(in_bytes));
     CU(fp.out_dev.ensure(out_bytes));
@@ -600,6 +656,19 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
     long long *sums_dev = (long long *)fp.out_dev.p;
     int *err_dev = (int *)(fp.out_dev.p + sizeof(long long) * total);
     unsigned *ctr_dev = (unsigned *)(fp.out_dev.p + sizeof(long long) * total + 8);
+    unsigned *done_dev = ctr_dev + n_groups;
+    // passes needed (a sweep group holds kMaxRows candidate rows per pass); the cross-GPU
+    // reduction is fused into the last one
+    size_t n_passes = 1;
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        size_t rows = 0;
+        for (size_t sw = (size_t)g * kMaxSweeps; sw < std::min(n_sweeps, ((size_t)g + 1) * kMaxSweeps); ++sw)
+            rows += n_cand[sw];
+        n_passes = std::max(n_passes, (rows + kMaxRows - 1) / kMaxRows);
+    }
+    fr_dev_comm *comm = pl->comm && pl->comm->world > 1 ? pl->comm : nullptr;
+    const bool fuse = comm && comm->mail.ok && total <= kMailWords;
+    size_t pass = 0;
     CU(cudaMemsetAsync(fp.out_dev.p, 0, out_bytes, s));
     if (out_per_query)
         CU(cudaMemsetAsync(pl->perq_dev.p, 0, sizeof(double) * total * (size_t)pl->nq_view, s));
@@ -659,7 +728,15 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         a.dm = (uint32_t)dm;
         a.err = err_dev;
         a.tile_ctr = ctr_dev;
-        if (pl->nt == 0) continue;
+        ++pass;
+        const bool fuse_now = fuse && pass == n_passes;
+        a.mail_peers = fuse_now ? comm->mail.peer_dev.p : nullptr;
+        a.done_ctr = done_dev;
+        a.mail_rank = comm ? (uint32_t)comm->rank : 0u;
+        a.mail_world = comm ? (uint32_t)comm->world : 1u;
+        a.mail_epoch = fuse_now ? ++comm->mail.epoch : 0u;
+        a.mail_words = (uint32_t)total;
+        if (pl->nt == 0 && !fuse_now) continue;
         // the weight table is staged in shared memory while that costs no resident CTA
         bool ws = SmemLayout(128, 1, ((a.dm + 7) & ~7u) * kMaxSweeps).total <= 56 * 1024;
         if (const char *env = getenv("FASTRANK_WSMEM")) ws = atoi(env) != 0;
@@ -677,7 +754,7 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         }
         if (rc) return 1;
     }
-    if (allreduce_sums(pl, sums_dev, total, s)) return 1;
+    if (!fuse && allreduce_sums(pl, sums_dev, total, s)) return 1;
     CU(cudaMemcpyAsync(fp.out_host.p, fp.out_dev.p, sizeof(long long) * total + 8, cudaMemcpyDeviceToHost, s));
     if (out_per_query)
         CU(cudaMemcpyAsync(out_per_query, pl->perq_dev.p, sizeof(double) * total * (size_t)pl->nq_view,
