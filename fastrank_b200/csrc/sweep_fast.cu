@@ -325,38 +325,11 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
             if (t == 0) s_misc[M_CTR] = 0;
         };
 
-        score_group(0);
-        __syncthreads();
-        for (int g = 0; g < G; ++g) {
-            slot_t *slots = s_slot0 + (size_t)(g & 1) * slot_stride;
-            const int nrow = min(32, R - (g << 5));  // live lanes of this group
-            // -- rank by counting; lane = row, TD documents per task --
-            {
-                int ti = 0;
-                if (lane == 0) ti = atomicAdd(&s_misc[M_CTR], 1);
-                ti = __shfl_sync(0xffffffffu, ti, 0);
-                while (ti < ntask) {
-                    int tnext = 0;
-                    if (lane == 0) tnext = atomicAdd(&s_misc[M_CTR], 1);
-                    const uint2 tk = s_tasks[ti];
-                    const int qs = (int)(tk.x & 0xffffu), qe = (int)(tk.x >> 16);
-                    const int t0 = (int)(tk.y & 0xffffu), n = (int)(tk.y >> 16);
-                    const unsigned len = (unsigned)(qe - qs);
-                    const unsigned lim =
-                        (P.metric == FR_METRIC_NDCG && (unsigned)P.depth < len) ? (unsigned)P.depth : len;
-                    const bool tag_cls = P.metric == FR_METRIC_NDCG && use_tbl;
-                    // a short last chunk of a query takes the half-width walk
-                    if (TD > 4 && n <= TD / 2)
-                        rank_task<(TD > 4 ? TD / 2 : TD), slot_t>(myrow, qs, qe, t0, n, lim, lane < nrow, tag_cls, s_cls,
-                                                                  slots, lane);
-                    else
-                        rank_task<TD, slot_t>(myrow, qs, qe, t0, n, lim, lane < nrow, tag_cls, s_cls, slots, lane);
-                    ti = __shfl_sync(0xffffffffu, tnext, 0);
-                }
-            }
-            __syncthreads();
-            // -- one warp per query folds the slots in rank order; then the next group's scores --
-            for (int ql = warp; ql < nqt; ql += TB / 32) {
+        // one warp folds one query of row group gq: slots in rank order -> value -> fixed point
+        auto fold_query = [&](int ql, int gq) {
+            const slot_t *slots = s_slot0 + (size_t)(gq & 1) * slot_stride;
+            const int nrow = min(32, R - (gq << 5));
+            const int g = gq;
                 const uint32_t pq = q0 + ql;
                 const uint32_t loc = P.pq_local[pq];
                 const uint32_t start = loc & 0xffffu, len = loc >> 16;
@@ -416,10 +389,52 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
                     const long long fx = __double2ll_rn(value * kFx);
                     atomicAdd(&s_sum[row], (unsigned long long)fx);
                 }
+                    };
+
+        score_group(0);
+        __syncthreads();
+        for (int g = 0; g < G; ++g) {
+            slot_t *slots = s_slot0 + (size_t)(g & 1) * slot_stride;
+            const int nrow = min(32, R - (g << 5));  // live lanes of this group
+            // -- rank by counting; lane = row, TD documents per task --
+            {
+                int ti = 0;
+                if (lane == 0) ti = atomicAdd(&s_misc[M_CTR], 1);
+                ti = __shfl_sync(0xffffffffu, ti, 0);
+                // queue = the previous group's folds (latency-bound: slot and table reads, a serial
+                // f64 sum, one division) followed by this group's ranking tasks (issue-bound)
+                const int nfold = g > 0 ? nqt : 0;
+                while (ti < nfold + ntask) {
+                    int tnext = 0;
+                    if (lane == 0) tnext = atomicAdd(&s_misc[M_CTR], 1);
+                    if (ti < nfold) {
+                        fold_query(ti, g - 1);
+                        ti = __shfl_sync(0xffffffffu, tnext, 0);
+                        continue;
+                    }
+                    const uint2 tk = s_tasks[ti - nfold];
+                    const int qs = (int)(tk.x & 0xffffu), qe = (int)(tk.x >> 16);
+                    const int t0 = (int)(tk.y & 0xffffu), n = (int)(tk.y >> 16);
+                    const unsigned len = (unsigned)(qe - qs);
+                    const unsigned lim =
+                        (P.metric == FR_METRIC_NDCG && (unsigned)P.depth < len) ? (unsigned)P.depth : len;
+                    const bool tag_cls = P.metric == FR_METRIC_NDCG && use_tbl;
+                    // a short last chunk of a query takes the half-width walk
+                    if (TD > 4 && n <= TD / 2)
+                        rank_task<(TD > 4 ? TD / 2 : TD), slot_t>(myrow, qs, qe, t0, n, lim, lane < nrow, tag_cls, s_cls,
+                                                                  slots, lane);
+                    else
+                        rank_task<TD, slot_t>(myrow, qs, qe, t0, n, lim, lane < nrow, tag_cls, s_cls, slots, lane);
+                    ti = __shfl_sync(0xffffffffu, tnext, 0);
+                }
             }
+            __syncthreads();
             if (g + 1 < G) score_group(g + 1);
             __syncthreads();
         }
+        // the last group's fold has no ranking phase left to hide in
+        for (int ql = warp; ql < nqt; ql += TB / 32) fold_query(ql, G - 1);
+        __syncthreads();
     }
     if (nan_seen) atomicOr(A.err, ERR_NAN_SCORE);
     __syncthreads();
@@ -485,7 +500,11 @@ int launch_fast(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStrea
         const auto key = std::make_pair(pl->ds->device, L.total);
         auto it = cache.find(key);
         if (it == cache.end()) {
-            CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+            // the attribute is a ceiling, not a reservation: raise it to the device maximum once
+            // (setting it per size would LOWER it when a smaller layout comes by later)
+            int optin = 0;
+            CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, pl->ds->device));
+            CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TB, L.total));
             it = cache.emplace(key, occ).first;
         }
