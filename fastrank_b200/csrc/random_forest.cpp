@@ -1,7 +1,8 @@
 // random_forest.cpp -- random-forest learner (random_forest.rs:14-408) on the host.
 //
-// Tree INDUCTION is host work (sort-by-feature and prefix statistics per node; SURVEY.md 2 row 5
-// keeps it off the GPU path); what the forest produces -- a WeightedEnsemble of regression
+// Tree INDUCTION is host work (per node: feature statistics, then per feature the partition
+// statistics of k-1 evenly spaced thresholds; SURVEY.md 2 row 5 keeps it off the GPU path); what
+// the forest produces -- a WeightedEnsemble of regression
 // trees -- is scored and evaluated on the GPU (device.cu model_score_kernel + scores_eval_kernel):
 // once per tree when the reference's per-tree evaluate_mean is observable (progress table,
 // weight_trees; random_forest.rs:315-318) and for every later evaluate / predict call.
@@ -10,7 +11,7 @@
 // per-tree seeds are drawn up front from the master generator exactly as the reference does, so
 // the result does not depend on the number of threads.  Where the reference's outcome depends on
 // unspecified order (sort_unstable among equal keys, HashMap iteration) this file picks the
-// deterministic choice: stable sorts, "last maximal element", parent query order.
+// deterministic choice: node order for sums, "last maximal element", parent query order.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -70,112 +71,132 @@ double compute_output(const Ctx &c, const uint32_t *ids, size_t n) {  // random_
     return sum / (double)n;
 }
 
-double squared_error(const Ctx &c, const uint32_t *ids, size_t n) {  // :42-51
-    const double output = compute_output(c, ids, n);
-    double sse = 0.0;
-    for (size_t i = 0; i < n; ++i) {
-        const double diff = output - c.gain(ids[i]);
-        sse += diff * diff;
-    }
-    return sse;
-}
-
-double positive_fraction(const Ctx &c, const uint32_t *ids, size_t n, double *p_no) {
-    size_t positive = 0;
-    for (size_t i = 0; i < n; ++i) positive += c.ds.gains[ids[i]] > 0.0f;
-    const double count = (double)n;
-    *p_no = (count - (double)positive) / count;
-    return (double)positive / count;
-}
-
-double gini_impurity(const Ctx &c, const uint32_t *ids, size_t n) {  // :52-66
-    if (n == 0) return 0.0;
-    double p_no;
-    const double p_yes = positive_fraction(c, ids, n, &p_no);
-    return p_yes * (1.0 - p_yes) + p_no * (1.0 - p_no);
-}
-
 double plogp(double x) { return x == 0.0 ? 0.0 : x * std::log2(x); }  // :67-73
-
-double entropy(const Ctx &c, const uint32_t *ids, size_t n) {  // :74-87
-    if (n == 0) return 0.0;
-    double p_no;
-    const double p_yes = positive_fraction(c, ids, n, &p_no);
-    return -plogp(p_yes) - plogp(p_no);
-}
-
-double label_variance(const Ctx &c, const uint32_t *ids, size_t n) {  // label_stats(..).unwrap().variance
-    StreamingStats st;
-    for (size_t i = 0; i < n; ++i) st.push(c.gain(ids[i]));
-    if (!st.finished()) throw Error("TrueVarianceReduction needs at least two instances on each side of a split");
-    return st.variance();
-}
-
-double importance(const Ctx &c, const uint32_t *lhs, size_t nl, const uint32_t *rhs, size_t nr) {  // :90-125
-    const std::string &m = c.p.split_method;
-    if (m == "SquaredError") return -(squared_error(c, lhs, nl) + squared_error(c, rhs, nr));
-    if (m == "BinaryGiniImpurity") return -(gini_impurity(c, lhs, nl) * (double)nl + gini_impurity(c, rhs, nr) * (double)nr);
-    if (m == "InformationGain") return -(entropy(c, lhs, nl) * (double)nl + entropy(c, rhs, nr) * (double)nr);
-    return -(label_variance(c, lhs, nl) * (double)nl + label_variance(c, rhs, nr) * (double)nr);
-}
 
 struct FeatureSplit {
     bool valid = false;
     uint32_t fid = 0;
     double split = 0.0, importance = 0.0;
-    std::vector<uint32_t> lhs, rhs;
+    size_t n_lhs = 0;
 };
 
-// random_forest.rs:211-286
+// random_forest.rs:211-286.  The reference sorts the node's instances by the feature and cuts
+// the sorted list at each of the k-1 evenly spaced thresholds; a cut at threshold p puts exactly
+// the instances with value < p on the left (the `while scores[i] < position` walk, :238-241).
+// The same partitions are produced here without the sort: one pass counts, per threshold, how
+// many values fall below it (that count is the reference's split position, so the "same
+// position as the previous threshold" de-duplication is identical), and the importance of each
+// surviving cut is accumulated over the instances in node order.  Only the order in which
+// floating-point sums are taken differs -- an order the reference leaves unspecified anyway
+// (sort_unstable among equal feature values).
 FeatureSplit generate_split_candidate(const Ctx &c, uint32_t fid, const std::vector<uint32_t> &instances,
-                                      const StreamingStats &fstats) {
+                                      const StreamingStats &fstats, const std::vector<double> &values) {
     FeatureSplit out;
-    StreamingStats labels;
-    for (uint32_t i : instances) labels.push(c.gain(i));
-    if (!labels.finished() || labels.max == labels.min) return out;
     const uint32_t k = c.p.split_candidates;
     const double range = fstats.max - fstats.min;
-    std::vector<std::pair<double, uint32_t>> by_value;
-    by_value.reserve(instances.size());
-    for (uint32_t i : instances) {
-        double v = 0.0;
-        c.feature_value(i, fid, &v);  // unwrap_or(0.0)
-        by_value.emplace_back(v, i);
+    const size_t n = instances.size();
+    std::vector<double> position;
+    for (uint32_t i = 1; i < k; ++i) position.push_back(((double)i / (double)k) * range + fstats.min);
+    const size_t m = position.size();
+    // below[i] = #{v < position[i]}; thresholds ascend, so count into the first bucket that
+    // holds the value and prefix-sum afterwards
+    std::vector<size_t> bucket(m + 1, 0);
+    for (size_t a = 0; a < n; ++a) {
+        const double v = values[a];
+        size_t b = 0;
+        while (b < m && !(v < position[b])) ++b;
+        bucket[b] += 1;
     }
-    std::stable_sort(by_value.begin(), by_value.end(),
-                     [](const auto &a, const auto &b) { return a.first < b.first; });
-    std::vector<uint32_t> ids(by_value.size());
-    for (size_t i = 0; i < by_value.size(); ++i) ids[i] = by_value[i].second;
-    // positions in the sorted order where each of the k-1 evenly spaced thresholds falls
-    std::vector<std::pair<double, size_t>> positions;
-    size_t at = 0;
-    for (uint32_t i = 1; i < k; ++i) {
-        const double f = (double)i / (double)k;
-        const double position = f * range + fstats.min;
-        while (at < ids.size() && by_value[at].first < position) ++at;
-        if (!positions.empty() && positions.back().second == at) continue;
-        positions.emplace_back(position, at);
-    }
-    bool have = false;
-    size_t best_pos = 0;
-    for (const auto &sp : positions) {
-        const size_t right = sp.second;
-        const size_t nl = right, nr = ids.size() - right;
-        if (nl < c.p.min_leaf_support || nr < c.p.min_leaf_support) continue;
-        const double imp = importance(c, ids.data(), nl, ids.data() + right, nr);
-        if (imp != imp) throw Error("split importance is NaN");
-        if (!have || imp >= out.importance) {  // sort by importance, take the last
-            have = true;
-            out.importance = imp;
-            out.split = sp.first;
-            best_pos = right;
+    std::vector<size_t> below(m, 0);
+    {
+        size_t run = 0;
+        for (size_t i = 0; i < m; ++i) {
+            run += bucket[i];
+            below[i] = run;
         }
     }
-    if (!have) return out;
+    std::vector<size_t> kept;  // thresholds that survive de-duplication and the leaf-size test
+    {
+        bool have_prev = false;
+        size_t prev = 0;
+        for (size_t i = 0; i < m; ++i) {
+            if (have_prev && prev == below[i]) continue;
+            have_prev = true;
+            prev = below[i];
+            const size_t nl = below[i], nr = n - below[i];
+            if (nl < c.p.min_leaf_support || nr < c.p.min_leaf_support) continue;
+            kept.push_back(i);
+        }
+    }
+    if (kept.empty()) return out;
+    const size_t q = kept.size();
+    const std::string &method = c.p.split_method;
+    std::vector<double> imp(q, 0.0);
+    if (method == "SquaredError") {  // :42-51, two passes like the reference: means, then squared errors
+        std::vector<double> suml(q, 0.0), sumr(q, 0.0), ssel(q, 0.0), sser(q, 0.0);
+        for (size_t a = 0; a < n; ++a) {
+            const double v = values[a], g = c.gain(instances[a]);
+            for (size_t e = 0; e < q; ++e) (v < position[kept[e]] ? suml[e] : sumr[e]) += g;
+        }
+        std::vector<double> meanl(q), meanr(q);
+        for (size_t e = 0; e < q; ++e) {
+            const size_t nl = below[kept[e]], nr = n - nl;
+            meanl[e] = nl ? suml[e] / (double)nl : 0.0;
+            meanr[e] = nr ? sumr[e] / (double)nr : 0.0;
+        }
+        for (size_t a = 0; a < n; ++a) {
+            const double v = values[a], g = c.gain(instances[a]);
+            for (size_t e = 0; e < q; ++e) {
+                if (v < position[kept[e]]) {
+                    const double diff = meanl[e] - g;
+                    ssel[e] += diff * diff;
+                } else {
+                    const double diff = meanr[e] - g;
+                    sser[e] += diff * diff;
+                }
+            }
+        }
+        for (size_t e = 0; e < q; ++e) imp[e] = -(ssel[e] + sser[e]);
+    } else if (method == "TrueVarianceReduction") {  // :115-122
+        std::vector<StreamingStats> sl(q), sr(q);
+        for (size_t a = 0; a < n; ++a) {
+            const double v = values[a], g = c.gain(instances[a]);
+            for (size_t e = 0; e < q; ++e) (v < position[kept[e]] ? sl[e] : sr[e]).push(g);
+        }
+        for (size_t e = 0; e < q; ++e) {
+            if (!sl[e].finished() || !sr[e].finished())
+                throw Error("TrueVarianceReduction needs at least two instances on each side of a split");
+            imp[e] = -(sl[e].variance() * (double)sl[e].n + sr[e].variance() * (double)sr[e].n);
+        }
+    } else {  // BinaryGiniImpurity :52-66,:95-103 / InformationGain :74-87,:104-112
+        std::vector<size_t> posl(q, 0), posr(q, 0);
+        for (size_t a = 0; a < n; ++a) {
+            if (!(c.ds.gains[instances[a]] > 0.0f)) continue;
+            const double v = values[a];
+            for (size_t e = 0; e < q; ++e) (v < position[kept[e]] ? posl[e] : posr[e]) += 1;
+        }
+        auto side = [&](size_t positive, size_t count) {
+            if (count == 0) return 0.0;
+            const double cnt = (double)count;
+            const double p_yes = (double)positive / cnt, p_no = (cnt - (double)positive) / cnt;
+            if (method == "BinaryGiniImpurity") return (p_yes * (1.0 - p_yes) + p_no * (1.0 - p_no)) * cnt;
+            return (-plogp(p_yes) - plogp(p_no)) * cnt;
+        };
+        for (size_t e = 0; e < q; ++e) {
+            const size_t nl = below[kept[e]], nr = n - nl;
+            imp[e] = -(side(posl[e], nl) + side(posr[e], nr));
+        }
+    }
+    size_t best = 0;
+    for (size_t e = 0; e < q; ++e) {
+        if (imp[e] != imp[e]) throw Error("split importance is NaN");
+        if (imp[e] >= imp[best]) best = e;  // sort by importance, take the last
+    }
     out.valid = true;
     out.fid = fid;
-    out.lhs.assign(ids.begin(), ids.begin() + best_pos);
-    out.rhs.assign(ids.begin() + best_pos, ids.end());
+    out.split = position[kept[best]];
+    out.importance = imp[best];
+    out.n_lhs = below[kept[best]];
     return out;
 }
 
@@ -200,18 +221,36 @@ std::unique_ptr<TreeNode> learn_recursive(const Ctx &c, const std::vector<uint32
             if (c.feature_value(inst, features[a], &v)) fstats[a].push(v);
         }
     }
+    // label statistics of the node (random_forest.rs:217-221), the same for every feature
+    StreamingStats labels;
+    for (uint32_t inst : instances) labels.push(c.gain(inst));
+    const bool splittable = labels.finished() && labels.max != labels.min;
     FeatureSplit best;
-    for (size_t a = 0; a < features.size(); ++a) {
+    std::vector<double> values(instances.size());
+    for (size_t a = 0; splittable && a < features.size(); ++a) {
         if (!fstats[a].finished()) continue;
-        FeatureSplit cand = generate_split_candidate(c, features[a], instances, fstats[a]);
+        for (size_t i = 0; i < instances.size(); ++i) {
+            double v = 0.0;
+            c.feature_value(instances[i], features[a], &v);  // unwrap_or(0.0), :226-229
+            values[i] = v;
+        }
+        FeatureSplit cand = generate_split_candidate(c, features[a], instances, fstats[a], values);
         if (!cand.valid) continue;
-        if (!best.valid || cand.importance >= best.importance) best = std::move(cand);
+        if (!best.valid || cand.importance >= best.importance) best = cand;
     }
     if (!best.valid) return nullptr;  // NoFeatureSplitCandidates
-    std::unique_ptr<TreeNode> lhs = learn_recursive(c, features, best.lhs, depth + 1);
-    if (!lhs) lhs = leaf(compute_output(c, best.lhs.data(), best.lhs.size()));
-    std::unique_ptr<TreeNode> rhs = learn_recursive(c, features, best.rhs, depth + 1);
-    if (!rhs) rhs = leaf(compute_output(c, best.rhs.data(), best.rhs.size()));
+    std::vector<uint32_t> lhs_ids, rhs_ids;
+    lhs_ids.reserve(best.n_lhs);
+    rhs_ids.reserve(instances.size() - best.n_lhs);
+    for (uint32_t inst : instances) {
+        double v = 0.0;
+        c.feature_value(inst, best.fid, &v);
+        (v < best.split ? lhs_ids : rhs_ids).push_back(inst);
+    }
+    std::unique_ptr<TreeNode> lhs = learn_recursive(c, features, lhs_ids, depth + 1);
+    if (!lhs) lhs = leaf(compute_output(c, lhs_ids.data(), lhs_ids.size()));
+    std::unique_ptr<TreeNode> rhs = learn_recursive(c, features, rhs_ids, depth + 1);
+    if (!rhs) rhs = leaf(compute_output(c, rhs_ids.data(), rhs_ids.size()));
     std::unique_ptr<TreeNode> node(new TreeNode());
     node->leaf = false;
     node->fid = best.fid;
