@@ -327,6 +327,11 @@ def run_ours(args, rank, world, local_rank):
                 "avg_launch_ms": avg_launch_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel_share_of_step": kern_ms / ms if ms > 0 else None, "peak_source": peak_src,
                 "evals_per_launch": EVALS_PER_STEP / launches_per_step,
+                # what actually bounds the kernel (from the committed ncu capture of this command)
+                "issue_slots_busy_frac": None if traffic is None or "issue_active_pct" not in traffic
+                else traffic["issue_active_pct"] / 100.0,
+                "fp64_pipe_busy_frac": None if traffic is None or "fp64_pipe_pct" not in traffic
+                else traffic["fp64_pipe_pct"] / 100.0,
                 "note": "one X pass is shared by all 8 restarts (204-408 candidate rankings per document per "
                         "launch), so the kernel is instruction-issue / FP64-compare bound, not HBM bound; "
                         "see DESIGN.md for the issue-slot roofline"}
