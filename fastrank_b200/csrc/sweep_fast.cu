@@ -236,8 +236,10 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     const double *myrow = s_score + (size_t)lane * ROW;
 
 
-    for (uint32_t tile = G > 0 ? (uint32_t)s_misc[M_TILE] : P.nt; tile < P.nt; tile = (uint32_t)s_misc[M_NEXT]) {
-        // the next tile is claimed now; the value is read after this tile's last barrier
+    uint32_t next_tile = P.nt;
+    for (uint32_t tile = G > 0 ? (uint32_t)s_misc[M_TILE] : P.nt; tile < P.nt; tile = next_tile) {
+        // the next tile is claimed now; every thread picks the value up BEFORE this tile's last
+        // barrier, so the claim after next cannot overtake a slow reader
         if (t == 0) s_misc[M_NEXT] = (int)atomicAdd(A.tile_ctr + blockIdx.y, 1u);
         const uint32_t doc0 = P.tile_doc_off[tile];
         const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
@@ -434,6 +436,7 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
         }
         // the last group's fold has no ranking phase left to hide in
         for (int ql = warp; ql < nqt; ql += TB / 32) fold_query(ql, G - 1);
+        next_tile = (uint32_t)s_misc[M_NEXT];
         __syncthreads();
     }
     if (nan_seen) atomicOr(A.err, ERR_NAN_SCORE);
