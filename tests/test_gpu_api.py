@@ -375,3 +375,58 @@ def test_forest_kernel_layouts_bit_exact(fr, oracle, monkeypatch):
         for spec in specs:
             got = fr.CModel.from_dict(spec).predict_dense(ds)
             assert np.array_equal(got, oracle.score_model(X, spec)), (env, list(spec)[0])
+
+
+def test_lifecycle_releases_device_memory_and_threads_share_a_dataset(fr, oracle):
+    """Handles own their GPU memory (free_dataset releases the matrix and every cached plan), and
+    concurrent calls on the same handles are safe, as with the reference's Arc-shared immutable
+    objects (cffi releases the GIL around native calls)."""
+    import gc
+    import threading
+
+    import torch
+
+    X, y, qid = synth(60000, 32, 1500, seed=51)
+
+    def cycle():
+        ds = fr.CDataset.from_numpy(X, y, qid)
+        m = fr.CModel.from_dict({"Linear": {"weights": [0.1 * (j % 5 - 2) for j in range(32)]}})
+        for measure in ("ndcg@10", "map", "rr", "ndcg"):
+            ds.evaluate_mean(m, measure)
+        del ds, m
+        gc.collect()
+
+    cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(6):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 8 << 20, (free0, free1)  # nothing accumulates
+
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    ods = oracle_dataset(oracle, X, y, qid)
+    rng = np.random.default_rng(1)
+    specs = [{"Linear": {"weights": [float(v) for v in rng.normal(size=32)]}} for _ in range(6)]
+    expected = [oracle.mean(oracle.evaluate_scores(ods, oracle.score_model(X, s), "ndcg@10")) for s in specs]
+    got = [None] * len(specs)
+    errors = []
+
+    def work(i):
+        try:
+            m = fr.CModel.from_dict(specs[i])
+            for _ in range(5):
+                got[i] = ds.evaluate_mean(m, "ndcg@10" if i % 2 == 0 else "ndcg@10")
+                ds.evaluate(m, "map")
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(specs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for g, e in zip(got, expected):
+        assert g == pytest.approx(e, abs=1e-12)
