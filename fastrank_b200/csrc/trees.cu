@@ -91,9 +91,39 @@ __global__ void __launch_bounds__(kTile) forest_tile_kernel(const float *__restr
 // 2i+1 / 2i+2, 8 bytes per node {fid, split}; a tree is one contiguous block
 //   [2^levels - 1 nodes][1 pad][2^levels f64 leaves]  =  2^(levels+4) bytes.
 // Shallow leaves are padded down to the last level (always-left dummy splits over copies of the
-// leaf value), so every walk takes exactly `levels` steps with no leaf test.  Trees are streamed
-// through shared memory in batches with double-buffered cp.async, so a walk never waits on L2:
-// every step is two shared-memory reads (node, feature) and a compare.
+// leaf value), so every walk takes exactly `levels` steps with no leaf test.  The X tile (one
+// 512-byte bulk copy per feature row) and the trees (double-buffered 16 KB batches) are moved by
+// the TMA copy engine (cp.async.bulk completing on mbarriers; one elected thread issues them), so
+// a walk never waits on L2: every step is two shared-memory reads (node, feature) and a compare.
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier -----------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 __global__ void __launch_bounds__(kTile) forest_heap_kernel(const float *__restrict__ x, size_t ld,
                                                             uint32_t dstage, size_t n,
                                                             const uint4 *__restrict__ heap,
@@ -103,40 +133,45 @@ __global__ void __launch_bounds__(kTile) forest_heap_kernel(const float *__restr
                                                             const uint32_t *__restrict__ inst_of_pos,
                                                             double *__restrict__ out_pos,
                                                             double *__restrict__ out_inst) {
-    extern __shared__ __align__(16) float xs[];  // [dstage][kTile], then 2 tree-batch buffers
+    extern __shared__ __align__(128) float xs[];  // [dstage][kTile], then 2 tree-batch buffers
+    __shared__ __align__(8) uint64_t bars[3];     // X tile, tree batches (double-buffered)
     const int t = threadIdx.x;
     const size_t p0 = (size_t)blockIdx.x * kTile;
-    const uint32_t tree_u4 = 1u << levels;          // 16-byte units per tree
-    const uint32_t batch_u4 = batch * tree_u4;      // ... per batch buffer
+    const uint32_t tree_u4 = 1u << levels;      // 16-byte units per tree
+    const uint32_t batch_u4 = batch * tree_u4;  // ... per batch buffer
     uint4 *tbuf = (uint4 *)(xs + (size_t)dstage * kTile);
     const uint32_t n_batches = (n_trees + batch - 1) / batch;
+    // one elected thread drives the copy engine: a 512-byte row of X per feature, 16 KB per batch
     auto stage_batch = [&](uint32_t b) {
         const uint32_t first = b * batch;
-        const uint32_t cnt = min(batch, n_trees - first) * tree_u4;
-        const uint4 *src = heap + (size_t)first * tree_u4;
-        uint4 *dst = tbuf + (size_t)(b & 1) * batch_u4;
-        for (uint32_t i = t; i < cnt; i += kTile) __pipeline_memcpy_async(dst + i, src + i, 16);
+        const uint32_t bytes = min(batch, n_trees - first) * tree_u4 * 16u;
+        mbar_expect_tx(&bars[1 + (b & 1)], bytes);
+        bulk_copy_g2s(tbuf + (size_t)(b & 1) * batch_u4, heap + (size_t)first * tree_u4, bytes, &bars[1 + (b & 1)]);
     };
-    {
-        const int col = (t & 31) * 4, r0 = t >> 5;
-        for (uint32_t f = r0; f < dstage; f += kTile / 32)
-            __pipeline_memcpy_async(xs + (size_t)f * kTile + col, x + (size_t)f * ld + p0 + col, 16);
+    if (t == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bars[0], dstage * kTile * (unsigned)sizeof(float));
+        for (uint32_t f = 0; f < dstage; ++f)
+            bulk_copy_g2s(xs + (size_t)f * kTile, x + (size_t)f * ld + p0, kTile * (unsigned)sizeof(float), &bars[0]);
         stage_batch(0);
-        __pipeline_commit();
     }
+    __syncthreads();  // barrier objects are initialised for everyone
+    mbar_wait(&bars[0], 0);
     const size_t p = p0 + t;
     const float *__restrict__ mine = xs + t;
-    const uint32_t n_internal = tree_u4 * 2 - 1;  // nodes are 8 bytes: 2 per 16-byte unit
     double acc = 0.0;
     for (uint32_t b = 0; b < n_batches; ++b) {
-        if (b + 1 < n_batches) {
+        if (t == 0 && b + 1 < n_batches) {
+            // the other buffer was last read (generic proxy) before the barrier that closed
+            // batch b - 1; order those reads before the async-proxy refill
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             stage_batch(b + 1);
-            __pipeline_commit();
-            __pipeline_wait_prior(1);
-        } else {
-            __pipeline_wait_prior(0);
         }
-        __syncthreads();
+        mbar_wait(&bars[1 + (b & 1)], (b >> 1) & 1u);
         const uint4 *cur = tbuf + (size_t)(b & 1) * batch_u4;
         const uint32_t first = b * batch, in_batch = min(batch, n_trees - first);
         for (uint32_t t0 = 0; t0 < in_batch; t0 += kWalkers) {
@@ -171,7 +206,6 @@ __global__ void __launch_bounds__(kTile) forest_heap_kernel(const float *__restr
         }
         __syncthreads();  // the buffer is refilled two batches from now
     }
-    (void)n_internal;
     if (p < n) {
         if (out_pos) out_pos[p] = acc;
         if (out_inst) out_inst[inst_of_pos[p]] = acc;
