@@ -26,7 +26,7 @@
 namespace {
 
 constexpr int kTile = 128;
-constexpr int kWalkers = 4;
+constexpr int kWalkers = 8;
 constexpr int kHeapLevels = 10;  // implicit-heap layout up to 1024 leaves per tree
 
 __global__ void __launch_bounds__(kTile) forest_tile_kernel(const float *__restrict__ x, size_t ld,
