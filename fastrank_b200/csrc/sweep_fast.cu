@@ -332,66 +332,66 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
             const slot_t *slots = s_slot0 + (size_t)(gq & 1) * slot_stride;
             const int nrow = min(32, R - (gq << 5));
             const int g = gq;
-                const uint32_t pq = q0 + ql;
-                const uint32_t loc = P.pq_local[pq];
-                const uint32_t start = loc & 0xffffu, len = loc >> 16;
-                const double norm = P.pq_norm[pq];
-                const slot_t *sl = slots + (size_t)start * 32 + lane;
-                double value = 0.0;
-                if (P.metric == FR_METRIC_NDCG) {
-                    if (norm == norm) {  // Some(ideal), evaluators.rs:351-358
-                        const uint32_t lim = len < (uint32_t)P.depth ? len : (uint32_t)P.depth;
-                        double dcg = 0.0;
-                        for (uint32_t r0 = 0; r0 < lim; r0 += 8) {
-                            unsigned id[8];
-                            double term[8];
+            const uint32_t pq = q0 + ql;
+            const uint32_t loc = P.pq_local[pq];
+            const uint32_t start = loc & 0xffffu, len = loc >> 16;
+            const double norm = P.pq_norm[pq];
+            const slot_t *sl = slots + (size_t)start * 32 + lane;
+            double value = 0.0;
+            if (P.metric == FR_METRIC_NDCG) {
+                if (norm == norm) {  // Some(ideal), evaluators.rs:351-358
+                    const uint32_t lim = len < (uint32_t)P.depth ? len : (uint32_t)P.depth;
+                    double dcg = 0.0;
+                    for (uint32_t r0 = 0; r0 < lim; r0 += 8) {
+                        unsigned id[8];
+                        double term[8];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) id[u] = r0 + u < lim ? sl[(size_t)(r0 + u) * 32] : 0u;
+                        for (int u = 0; u < 8; ++u) id[u] = r0 + u < lim ? sl[(size_t)(r0 + u) * 32] : 0u;
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                term[u] = 0.0;
-                                if (id[u]) {
-                                    const uint32_t r = r0 + u;
-                                    if (use_tbl)
-                                        term[u] = tbl[(size_t)(id[u] - 1) * F.tbl_r + r];
-                                    else
-                                        term[u] = s_gexp[id[u] - 1] / __ldg(P.lg2 + r);
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) dcg = __dadd_rn(dcg, term[u]);
-                        }
-                        if (dcg > norm) atomicOr(A.err, ERR_DCG_ABOVE_IDEAL);
-                        value = dcg / norm;
-                    }
-                } else if (P.metric == FR_METRIC_AP) {
-                    if (norm > 0.0) {
-                        unsigned recall = 0;
-                        double sum = 0.0;
-                        for (uint32_t r = 0; r < len; ++r) {
-                            if (sl[(size_t)r * 32]) {
-                                recall += 1;
-                                sum = __dadd_rn(sum, (double)recall / (double)(r + 1));
+                        for (int u = 0; u < 8; ++u) {
+                            term[u] = 0.0;
+                            if (id[u]) {
+                                const uint32_t r = r0 + u;
+                                if (use_tbl)
+                                    term[u] = tbl[(size_t)(id[u] - 1) * F.tbl_r + r];
+                                else
+                                    term[u] = s_gexp[id[u] - 1] / __ldg(P.lg2 + r);
                             }
                         }
-                        value = sum / norm;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) dcg = __dadd_rn(dcg, term[u]);
                     }
-                } else {
+                    if (dcg > norm) atomicOr(A.err, ERR_DCG_ABOVE_IDEAL);
+                    value = dcg / norm;
+                }
+            } else if (P.metric == FR_METRIC_AP) {
+                if (norm > 0.0) {
+                    unsigned recall = 0;
+                    double sum = 0.0;
                     for (uint32_t r = 0; r < len; ++r) {
                         if (sl[(size_t)r * 32]) {
-                            value = 1.0 / (double)(r + 1);
-                            break;
+                            recall += 1;
+                            sum = __dadd_rn(sum, (double)recall / (double)(r + 1));
                         }
                     }
+                    value = sum / norm;
                 }
-                if (lane < nrow) {
-                    const int row = (g << 5) + lane;
-                    if (A.perq)
-                        A.perq[(size_t)A.row_out[row0 + row] * P.nq_view + P.pq_view[pq]] = value;
-                    const long long fx = __double2ll_rn(value * kFx);
-                    atomicAdd(&s_sum[row], (unsigned long long)fx);
+            } else {
+                for (uint32_t r = 0; r < len; ++r) {
+                    if (sl[(size_t)r * 32]) {
+                        value = 1.0 / (double)(r + 1);
+                        break;
+                    }
                 }
-                    };
+            }
+            if (lane < nrow) {
+                const int row = (g << 5) + lane;
+                if (A.perq)
+                    A.perq[(size_t)A.row_out[row0 + row] * P.nq_view + P.pq_view[pq]] = value;
+                const long long fx = __double2ll_rn(value * kFx);
+                atomicAdd(&s_sum[row], (unsigned long long)fx);
+            }
+                };
 
         score_group(0);
         __syncthreads();

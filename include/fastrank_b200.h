@@ -182,7 +182,10 @@ int fr_dev_eval_coord_sweeps(fr_dev_plan *plan, size_t n_sweeps, const double *b
  * from dense_dataset.rs:67-76).  Ranking, tie-break, metric terms and their summation order are
  * the reference's, so per-query values are bit-identical to the exact path whenever the ranking
  * is.  This is what train_model uses (FASTRANK_SWEEP=exact selects the entry point above
- * instead).  out_per_query: NULL or n_sweeps x cand_stride x n_queries (view order). */
+ * instead); it submits all three directions of a line search (1 + 2 * num_max_iterations
+ * candidates per restart) in one call.  Requires queries of at most 256 documents
+ * (fr_dev_plan_has_fast_sweep).  out_per_query: NULL or n_sweeps x cand_stride x n_queries
+ * (view order). */
 int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *plan, size_t n_sweeps, const double *base_w,
                                   size_t wlen, const uint32_t *fid, const double *cand_w,
                                   const uint32_t *n_cand, size_t cand_stride, int64_t *out_sum_fx,
@@ -203,7 +206,10 @@ int fr_dev_eval_model(fr_dev_plan *plan, const fr_dev_model *m, int64_t *out_sum
 
 /* NCCL bootstrap: rank 0 calls fr_dev_comm_unique_id, ships the 128 bytes to every rank by
  * any means (torch.distributed in fastrank_b200/dist.py), then all ranks call
- * fr_dev_comm_create. */
+ * fr_dev_comm_create.  Creation also maps every peer's mailbox through CUDA IPC so that
+ * fr_dev_eval_coord_sweeps_fast can finish its cross-GPU sum inside the kernel over NVLink peer
+ * memory; when that mapping is unavailable anywhere (or FASTRANK_P2P=0) every rank stays on the
+ * ncclAllReduce path.  Either way sums are integers: results do not depend on the GPU count. */
 int fr_dev_comm_unique_id(uint8_t out_id[128]);
 int fr_dev_comm_create(int device, int rank, int world, const uint8_t id[128], fr_dev_comm **out);
 void fr_dev_comm_destroy(fr_dev_comm *comm);
