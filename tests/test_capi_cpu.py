@@ -167,3 +167,28 @@ def test_compute_fails_loudly_without_gpu(fr, golden_dir):
                  lambda: rd.evaluate_mean(m, "map"), lambda: m.predict_dense(rd)):
         with pytest.raises(Exception, match="no CUDA device|no CPU fallback"):
             call()
+
+
+def test_compat_package_exposes_the_reference_names():
+    # compat/ on PYTHONPATH makes `import fastrank` resolve to this implementation
+    import importlib
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "compat"))
+    try:
+        sys.modules.pop("fastrank", None)
+        fastrank = importlib.import_module("fastrank")
+        from fastrank.clib import CDataset, CModel, CQRel  # noqa: F401
+        from fastrank.training import CoordinateAscentParams, RandomForestParams, TrainRequest  # noqa: F401
+
+        for name in ("CQRel", "CDataset", "CModel", "query_json", "TrainRequest", "CoordinateAscentParams",
+                     "RandomForestParams"):
+            assert hasattr(fastrank, name), name
+        req = fastrank.TrainRequest.coordinate_ascent()
+        assert req.params.num_restarts == 5 and req.measure == "ndcg"
+    finally:
+        sys.path.remove(os.path.join(root, "compat"))
+        for k in [k for k in sys.modules if k == "fastrank" or k.startswith("fastrank.")]:
+            sys.modules.pop(k)
