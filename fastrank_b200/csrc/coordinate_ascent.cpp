@@ -147,17 +147,35 @@ Model coordinate_ascent_learn(const CoordinateAscentParams &p, const DatasetView
     std::vector<double> base_w, cand_w;
     std::vector<uint32_t> fid_arr, ncand;
     std::vector<int64_t> sums;
+    // One submitted line search.  A restart submits the line search of its current feature and,
+    // when the launch has room (fewer active restarts than the kernel serves per pass over X),
+    // LOOKAHEAD line searches for the features that follow in its shuffled order, built from the
+    // same best model.  They are valid exactly when the earlier features leave the best model
+    // untouched -- which is what the last pass of every restart looks like -- and are discarded
+    // otherwise.
+    struct Sweep {
+        size_t slot;        // index into `active`
+        uint32_t feature;
+        double orig;
+        size_t n_a;         // candidates of directions 0 and -1
+        bool has_b;         // direction +1 rides along
+        std::vector<double> cands;
+    };
+    const size_t kLaunchSweeps = 8;  // sweeps sharing one pass over X in fr_dev_eval_coord_sweeps_fast
+    // Opt-in (FASTRANK_LOOKAHEAD=1): on the 1M-document benchmark it cuts the launches of a
+    // training run by 28 % but scores 9 % more candidates, which nets out to nothing on one GPU.
+    bool lookahead = false;
+    if (const char *env = getenv("FASTRANK_LOOKAHEAD")) lookahead = speculate && atoi(env) != 0;
     std::vector<Restart *> active;
+    std::vector<Sweep> sweeps;
     for (;;) {
         active.clear();
         for (Restart &r : rs)
             if (!r.done) active.push_back(&r);
         if (active.empty()) break;
-        // 1. every active restart prepares its next group of candidates
-        base_w.assign(active.size() * dim, 0.0);
-        cand_w.assign(active.size() * stride, 0.0);
-        fid_arr.assign(active.size(), 0);
-        ncand.assign(active.size(), 0);
+        // 1. every active restart prepares its next group(s) of candidates
+        sweeps.clear();
+        const size_t extra = lookahead && active.size() < kLaunchSweeps ? kLaunchSweeps / active.size() - 1 : 0;
         for (size_t a = 0; a < active.size(); ++a) {
             Restart &r = *active[a];
             if (r.group == 0) {
@@ -171,71 +189,102 @@ Model coordinate_ascent_learn(const CoordinateAscentParams &p, const DatasetView
                         printf("----------------------------------------\n");
                     }
                 }
-                r.feature = r.order[r.fi];
-                r.start_score = r.best_score;
                 r.model = r.best_w;
                 if (p.normalize) l1_normalize(r.model);  // :134-138 (the clone, not the best)
-                r.orig = r.model[r.feature];
-                r.cands.clear();
-                direction_candidates(p, r.orig, 0, r.cands);
-                direction_candidates(p, r.orig, -1, r.cands);
-                r.n_a = r.cands.size();
-                r.has_b = speculate;
-                if (r.has_b) direction_candidates(p, r.orig, +1, r.cands);
-            } else {
-                r.cands.clear();
-                direction_candidates(p, r.orig, +1, r.cands);
+                const size_t n_here = std::min(1 + extra, r.order.size() - r.fi);
+                for (size_t m = 0; m < n_here; ++m) {
+                    Sweep sw;
+                    sw.slot = a;
+                    sw.feature = r.order[r.fi + m];
+                    sw.orig = r.model[sw.feature];
+                    direction_candidates(p, sw.orig, 0, sw.cands);
+                    direction_candidates(p, sw.orig, -1, sw.cands);
+                    sw.n_a = sw.cands.size();
+                    sw.has_b = speculate;
+                    if (sw.has_b) direction_candidates(p, sw.orig, +1, sw.cands);
+                    sweeps.push_back(std::move(sw));
+                }
+            } else {  // direction +1 of the feature whose directions 0 / -1 did not improve
+                Sweep sw;
+                sw.slot = a;
+                sw.feature = r.feature;
+                sw.orig = r.orig;
+                sw.n_a = 0;
+                sw.has_b = false;
+                direction_candidates(p, r.orig, +1, sw.cands);
+                sweeps.push_back(std::move(sw));
             }
-            std::copy(r.model.begin(), r.model.end(), base_w.begin() + a * dim);
-            std::copy(r.cands.begin(), r.cands.end(), cand_w.begin() + a * stride);
-            fid_arr[a] = r.feature;
-            ncand[a] = (uint32_t)r.cands.size();
-            stats.evals_computed += r.cands.size();
         }
-        // 2. one GPU pass over the feature matrix for all restarts (batched sweep); the
+        base_w.assign(sweeps.size() * dim, 0.0);
+        cand_w.assign(sweeps.size() * stride, 0.0);
+        fid_arr.assign(sweeps.size(), 0);
+        ncand.assign(sweeps.size(), 0);
+        for (size_t i = 0; i < sweeps.size(); ++i) {
+            const Sweep &sw = sweeps[i];
+            const Restart &r = *active[sw.slot];
+            std::copy(r.model.begin(), r.model.end(), base_w.begin() + i * dim);
+            std::copy(sw.cands.begin(), sw.cands.end(), cand_w.begin() + i * stride);
+            fid_arr[i] = sw.feature;
+            ncand[i] = (uint32_t)sw.cands.size();
+            stats.evals_computed += sw.cands.size();
+        }
+        // 2. one GPU pass over the feature matrix for all of them (batched sweep); the
         //    exact-order kernel (one pass per restart) on request or for very long queries
-        sums.assign(active.size() * stride, 0);
+        sums.assign(sweeps.size() * stride, 0);
         const auto t_dev = std::chrono::steady_clock::now();
         const int rc = use_fast
-                           ? fr_dev_eval_coord_sweeps_fast(ev.plan(), active.size(), base_w.data(), dim,
+                           ? fr_dev_eval_coord_sweeps_fast(ev.plan(), sweeps.size(), base_w.data(), dim,
                                                            fid_arr.data(), cand_w.data(), ncand.data(),
                                                            stride, sums.data(), nullptr)
-                           : fr_dev_eval_coord_sweeps(ev.plan(), active.size(), base_w.data(), dim,
+                           : fr_dev_eval_coord_sweeps(ev.plan(), sweeps.size(), base_w.data(), dim,
                                                       fid_arr.data(), cand_w.data(), ncand.data(), stride,
                                                       sums.data());
         stats.seconds_device += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_dev).count();
         if (rc) throw Error(fr_dev_last_error());
-        stats.sweeps += active.size();
+        stats.sweeps += sweeps.size();
         stats.global_steps += 1;
         // 3. replay the reference's sequential control flow on the means
-        for (size_t a = 0; a < active.size(); ++a) {
+        for (size_t i = 0; i < sweeps.size();) {
+            const size_t a = sweeps[i].slot;
             Restart &r = *active[a];
-            const std::string fname = p.quiet ? std::string() : view.parent->feature_name(r.feature);
-            auto take = [&](size_t k) {
-                const double score = ev.mean_from_fx(sums[a * stride + k]);
-                stats.evals_consumed += 1;
-                if (replace_if_better(r, score, r.cands[k]) && !p.quiet)
-                    printf("%4u|%-16s|%9.3f|%9.3f\n", r.id, fname.c_str(), r.cands[k], score);
-            };
-            bool feature_done = false;
-            if (r.group == 0) {
-                take(0);  // direction 0
-                if ((r.best_score - r.start_score) > p.tolerance) {
-                    feature_done = true;  // :174-176
-                } else {
-                    for (size_t k = 1; k < r.n_a; ++k) take(k);  // direction -1
-                    if ((r.best_score - r.start_score) > p.tolerance) feature_done = true;
-                    else if (T == 0) feature_done = true;
-                    else if (r.has_b) {
-                        for (size_t k = r.n_a; k < r.cands.size(); ++k) take(k);  // direction +1
-                        feature_done = true;
-                    } else r.group = 1;
+            size_t end = i;
+            while (end < sweeps.size() && sweeps[end].slot == a) ++end;
+            for (size_t cur = i; cur < end; ++cur) {
+                const Sweep &sw = sweeps[cur];
+                bool best_changed = false;
+                if (r.group == 0) {
+                    r.feature = sw.feature;
+                    r.orig = sw.orig;
+                    r.start_score = r.best_score;
                 }
-            } else {
-                for (size_t k = 0; k < r.cands.size(); ++k) take(k);  // direction +1
-                feature_done = true;
-            }
-            if (feature_done) {
+                const std::string fname = p.quiet ? std::string() : view.parent->feature_name(r.feature);
+                auto take = [&](size_t k) {
+                    const double score = ev.mean_from_fx(sums[cur * stride + k]);
+                    stats.evals_consumed += 1;
+                    if (replace_if_better(r, score, sw.cands[k])) {
+                        best_changed = true;
+                        if (!p.quiet) printf("%4u|%-16s|%9.3f|%9.3f\n", r.id, fname.c_str(), sw.cands[k], score);
+                    }
+                };
+                bool feature_done = false;
+                if (r.group == 0) {
+                    take(0);  // direction 0
+                    if ((r.best_score - r.start_score) > p.tolerance) {
+                        feature_done = true;  // :174-176
+                    } else {
+                        for (size_t k = 1; k < sw.n_a; ++k) take(k);  // direction -1
+                        if ((r.best_score - r.start_score) > p.tolerance) feature_done = true;
+                        else if (T == 0) feature_done = true;
+                        else if (sw.has_b) {
+                            for (size_t k = sw.n_a; k < sw.cands.size(); ++k) take(k);  // direction +1
+                            feature_done = true;
+                        } else r.group = 1;
+                    }
+                } else {
+                    for (size_t k = 0; k < sw.cands.size(); ++k) take(k);  // direction +1
+                    feature_done = true;
+                }
+                if (!feature_done) break;  // direction +1 follows in the next submission
                 if ((r.best_score - r.start_score) > p.tolerance) r.successes += 1;  // :181-183
                 r.group = 0;
                 r.fi += 1;
@@ -243,8 +292,12 @@ Model coordinate_ascent_learn(const CoordinateAscentParams &p, const DatasetView
                     r.fi = 0;
                     if (r.successes == 0) r.done = true;  // :185-187
                     else if (!p.quiet) printf("---------------------------\n");
+                    break;  // the next pass starts with a new shuffle
                 }
+                // a lookahead result stands only if this feature left the best model untouched
+                if (best_changed) break;
             }
+            i = end;
         }
     }
     if (!p.quiet) printf("---------------------------\nFinished successfully.\n");

@@ -430,3 +430,31 @@ def test_lifecycle_releases_device_memory_and_threads_share_a_dataset(fr, oracle
     assert not errors, errors
     for g, e in zip(got, expected):
         assert g == pytest.approx(e, abs=1e-12)
+
+
+def test_training_schedules_agree(fr, monkeypatch):
+    """The submission schedule (direction +1 merged into the launch, lookahead line searches that
+    fill idle launch capacity) is an execution detail: the model must come out bit for bit the
+    same as with one submission per direction group, and the consumed-evaluation count -- what
+    the reference's control flow evaluates -- must not move."""
+    X, y, qid = synth(30000, 24, 900, seed=61)
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    req = fr.TrainRequest.coordinate_ascent()
+    req.measure = "ndcg@10"
+    req.params.num_restarts, req.params.seed, req.params.quiet = 3, 11, True
+    results = {}
+    for label, env in (("default", {}), ("lookahead", {"FASTRANK_LOOKAHEAD": "1"}),
+                       ("no_speculation", {"FASTRANK_SPECULATE": "0"}), ("exact", {"FASTRANK_SWEEP": "exact"})):
+        for k in ("FASTRANK_LOOKAHEAD", "FASTRANK_SPECULATE", "FASTRANK_SWEEP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        model = ds.train_model(req)
+        stats = fr.query_json("last_train_stats")
+        results[label] = (model.to_dict()["Linear"]["weights"], stats["evals_consumed"], stats["global_steps"])
+    base = results["no_speculation"]
+    for label in ("default", "lookahead", "exact"):
+        assert results[label][0] == base[0], label
+        assert results[label][1] == base[1], label
+    # and the schedules really differ in how many launches they need
+    assert results["lookahead"][2] <= results["default"][2] < results["no_speculation"][2]
