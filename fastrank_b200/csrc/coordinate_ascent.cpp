@@ -5,7 +5,7 @@
 // to 1 + 2*T times per feature, one weight vector at a time.  The candidate weights of a
 // feature depend only on (orig, step_base, step_scale, T), never on a score, so here every
 // restart submits its whole next group of candidates to the GPU at once
-// (fr_dev_eval_coord_sweeps: one pass over the feature matrix per restart and group), and the
+// (fr_dev_eval_coord_sweeps_fast: ONE pass over the feature matrix for all restarts), and the
 // reference's sequential accept / early-break logic is replayed on the returned means.
 //   group A = direction 0 (weight -> 0) + direction -1   (1 + T candidates)
 //   group B = direction +1                               (T candidates), which the reference
@@ -53,9 +53,6 @@ struct Restart {
     double orig = 0.0;
     uint32_t feature = 0;
     int group = 0;  // 0 = A pending, 1 = B pending
-    size_t n_a = 0;        // candidates of group A in `cands`
-    bool has_b = false;    // group B rides along speculatively in the same submission
-    std::vector<double> cands;
     explicit Restart(unsigned __int128 seed) : rng(seed) {}
 };
 
