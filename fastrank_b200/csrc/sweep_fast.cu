@@ -215,19 +215,23 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
         for (uint32_t idx = t; idx < F.n_cls * F.tbl_r; idx += TB) s_tbl[idx] = F.disc_tbl[idx];
     if (WS)
         for (uint32_t idx = t; idx < dm8 * NS; idx += TB) s_w[idx] = wg[idx];
-    if (t == 0) {
-        // first row of every sweep (rows are sorted by sweep), and the coordinates that split a sum
-        int r = 0;
-        for (int s = 0; s <= NS; ++s) {
-            while (r < R && (int)A.row_meta[row0 + r] < s) ++r;
-            s_misc[M_SWROW + s] = r;
+    __syncthreads();
+    if (t <= NS) {
+        // first row of sweep t (rows are sorted by sweep): lower bound in the staged row table
+        int lo = 0, hi = R;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)s_rowsw[mid] < t) lo = mid + 1;
+            else hi = mid;
         }
-        for (int s = 0; s < NS; ++s) {
-            const bool has_rows = s_misc[M_SWROW + s + 1] > s_misc[M_SWROW + s];
-            s_misc[M_F + s] = (s < ns && has_rows) ? (int)A.fid[s0 + s] : -1;
-        }
-        s_misc[M_TILE] = (int)atomicAdd(A.tile_ctr + blockIdx.y, 1u);
+        s_misc[M_SWROW + t] = lo;
     }
+    __syncthreads();
+    if (t < NS) {
+        const bool has_rows = s_misc[M_SWROW + t + 1] > s_misc[M_SWROW + t];
+        s_misc[M_F + t] = (t < ns && has_rows) ? (int)A.fid[s0 + t] : -1;
+    }
+    if (t == 0) s_misc[M_TILE] = (int)atomicAdd(A.tile_ctr + blockIdx.y, 1u);
     __syncthreads();
     uint32_t fs[NS];
 #pragma unroll
@@ -236,11 +240,25 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     const double *myrow = s_score + (size_t)lane * ROW;
 
 
-    uint32_t next_tile = P.nt;
-    for (uint32_t tile = G > 0 ? (uint32_t)s_misc[M_TILE] : P.nt; tile < P.nt; tile = next_tile) {
-        // the next tile is claimed now; every thread picks the value up BEFORE this tile's last
+    // Work items: whole tiles first; the last n_split tiles are handed out as quarter items (a
+    // quarter of the row groups each, phase 1 repeated) so that the final wave of the persistent
+    // grid is made of short items and the SMs drain together.
+    const uint32_t n_split = G >= 4 ? min(P.nt, gridDim.x / 4u) : 0u;
+    const uint32_t n_whole = P.nt - n_split;
+    const uint32_t n_items = G > 0 ? n_whole + 4u * n_split : 0u;
+    uint32_t next_item = n_items;
+    for (uint32_t item = G > 0 ? (uint32_t)s_misc[M_TILE] : n_items; item < n_items; item = next_item) {
+        // the next item is claimed now; every thread picks the value up BEFORE this item's last
         // barrier, so the claim after next cannot overtake a slow reader
         if (t == 0) s_misc[M_NEXT] = (int)atomicAdd(A.tile_ctr + blockIdx.y, 1u);
+        uint32_t tile = item;
+        int g_begin = 0, g_end = G;
+        if (item >= n_whole) {
+            const uint32_t j = item - n_whole, part = j & 3u;
+            tile = n_whole + (j >> 2);
+            g_begin = (int)((uint32_t)G * part / 4u);
+            g_end = (int)((uint32_t)G * (part + 1u) / 4u);
+        }
         const uint32_t doc0 = P.tile_doc_off[tile];
         const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
         const bool active = t < nd;
@@ -393,9 +411,9 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
             }
                 };
 
-        score_group(0);
+        score_group(g_begin);
         __syncthreads();
-        for (int g = 0; g < G; ++g) {
+        for (int g = g_begin; g < g_end; ++g) {
             slot_t *slots = s_slot0 + (size_t)(g & 1) * slot_stride;
             const int nrow = min(32, R - (g << 5));  // live lanes of this group
             // -- rank by counting; lane = row, TD documents per task --
@@ -405,7 +423,7 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
                 ti = __shfl_sync(0xffffffffu, ti, 0);
                 // queue = the previous group's folds (latency-bound: slot and table reads, a serial
                 // f64 sum, one division) followed by this group's ranking tasks (issue-bound)
-                const int nfold = g > 0 ? nqt : 0;
+                const int nfold = g > g_begin ? nqt : 0;
                 while (ti < nfold + ntask) {
                     int tnext = 0;
                     if (lane == 0) tnext = atomicAdd(&s_misc[M_CTR], 1);
@@ -431,12 +449,12 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
                 }
             }
             __syncthreads();
-            if (g + 1 < G) score_group(g + 1);
+            if (g + 1 < g_end) score_group(g + 1);
             __syncthreads();
         }
         // the last group's fold has no ranking phase left to hide in
-        for (int ql = warp; ql < nqt; ql += TB / 32) fold_query(ql, G - 1);
-        next_tile = (uint32_t)s_misc[M_NEXT];
+        for (int ql = warp; ql < nqt; ql += TB / 32) fold_query(ql, g_end - 1);
+        next_item = (uint32_t)s_misc[M_NEXT];
         __syncthreads();
     }
     if (nan_seen) atomicOr(A.err, ERR_NAN_SCORE);
