@@ -352,19 +352,33 @@ DatasetView make_dense(size_t n, size_t d, const float *x, const double *y, cons
     ds->x = x;
     ds->dense_source = true;
     ds->gains.resize(n);
-    std::vector<std::string> names(n);
-    std::unordered_map<int64_t, std::string> cache;
+    ds->query_of.resize(n);
+    // query ids are interned as integers (dense_dataset.rs:33-47 keeps u32 ids and a name table);
+    // consecutive rows of one query -- the usual layout -- skip the hash lookup
+    std::unordered_map<int64_t, uint32_t> number_of;
+    int64_t last_qid = -1;
+    uint32_t last_number = 0;
     for (size_t i = 0; i < n; ++i) {
-        if (qids[i] < 0 || qids[i] > 0xFFFFFFFFll) throw Error("TryFromIntError(())");
+        const int64_t q = qids[i];
+        if (q < 0 || q > 0xFFFFFFFFll) throw Error("TryFromIntError(())");
         if (y[i] != y[i]) throw Error("NaN in ys[" + std::to_string(i) + "]");
         ds->gains[i] = (float)y[i];  // dense_dataset.rs:120
-        auto it = cache.find(qids[i]);
-        if (it == cache.end()) it = cache.emplace(qids[i], std::to_string(qids[i])).first;
-        names[i] = it->second;
+        if (q != last_qid) {
+            auto it = number_of.find(q);
+            if (it == number_of.end()) {
+                it = number_of.emplace(q, (uint32_t)ds->query_names.size()).first;
+                ds->query_names.push_back(std::to_string(q));
+                ds->query_lookup.emplace(ds->query_names.back(), it->second);
+                ds->by_query.emplace_back();
+            }
+            last_qid = q;
+            last_number = it->second;
+        }
+        ds->query_of[i] = last_number;
+        ds->by_query[last_number].push_back((uint32_t)i);
     }
     ds->features.resize(d);
     for (size_t j = 0; j < d; ++j) ds->features[j] = (uint32_t)j;
-    index_queries(*ds, names);
     DatasetView view;
     view.parent = ds;
     return view;

@@ -20,6 +20,8 @@
 // Determinism: per-query metric values are bit-identical to the oracle; they are summed as
 // signed fixed point (2^-40) with integer atomics, so the mean does not depend on launch
 // geometry, atomics order or the number of GPUs.
+#include <thread>
+
 #include "device_common.cuh"
 
 // =========================================================================================
@@ -595,6 +597,23 @@ int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const 
     ds->ld = (n + 127) / 128 * 128;
     ds->nq = n_queries;
     CU(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
+    // The row-major matrix goes up on a helper thread (a pageable copy blocks its caller for the
+    // whole transfer) while this thread builds the query / gain ordering the transpose needs.
+    DevBuf<float> staging;
+    CU(staging.alloc(n * d));
+    CU(ds->x.alloc(ds->ld * d));
+    cudaError_t copy_status = cudaSuccess;
+    std::thread copier([&]() {
+        copy_status = cudaSetDevice(device);
+        if (copy_status == cudaSuccess)
+            copy_status = cudaMemcpyAsync(staging.p, x, sizeof(float) * n * d, cudaMemcpyHostToDevice, ds->stream);
+    });
+    struct Joiner {
+        std::thread &t;
+        ~Joiner() {
+            if (t.joinable()) t.join();
+        }
+    } joiner{copier};
     // group by query (counting sort keeps instance ids ascending), then stable-sort each query
     // by gain: the reference's tie-break order (evaluators.rs:40-48)
     ds->q_len.assign(n_queries, 0);
@@ -642,11 +661,9 @@ int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const 
     CU(ds->gain.upload(ds->gain_pos, s));
     CU(ds->gexp.upload(gexp, s));
     CU(ds->inst_of_pos_dev.upload(ds->inst_of_pos, s));
-    CU(ds->x.alloc(ds->ld * d));
+    copier.join();
+    CU(copy_status);
     {
-        DevBuf<float> staging;
-        CU(staging.alloc(n * d));
-        CU(cudaMemcpyAsync(staging.p, x, sizeof(float) * n * d, cudaMemcpyHostToDevice, s));
         dim3 grid((unsigned)((ds->ld + 31) / 32), (unsigned)((d + 31) / 32));
         gather_transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(staging.p, ds->inst_of_pos_dev.p,
                                                             ds->x.p, n, d, ds->ld);
