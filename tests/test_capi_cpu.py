@@ -192,3 +192,32 @@ def test_compat_package_exposes_the_reference_names():
         sys.path.remove(os.path.join(root, "compat"))
         for k in [k for k in sys.modules if k == "fastrank" or k.startswith("fastrank.")]:
             sys.modules.pop(k)
+
+
+def _load_text(fr, tmp_path, text, name="t.libsvm"):
+    path = tmp_path / name
+    path.write_text(text)
+    return fr.CDataset.open_ranksvm(str(path))
+
+
+def test_libsvm_parser_cases(fr, tmp_path):
+    """The reference's libsvm.rs parser tests (libsvm.rs:318-432) through load_ranksvm_format:
+    qid handling, unsorted features, comments as document names, and every parse error."""
+    ds = _load_text(fr, tmp_path, "1 qid:A 1:1 2:1 3:1 # docA\n2 qid:B 6:1 3:1 4:0.5\n0 qid:A 2:7\n")
+    assert ds.num_instances() == 3
+    assert ds.queries() == {"A", "B"}
+    assert sorted(len(v) for v in ds.instances_by_query().values()) == [1, 2]
+    assert 6 in ds.feature_ids() and 1 in ds.feature_ids()
+    for text, what in (
+        ("1 qid:A what\n", "FeatureNoColon"),
+        ("1 qid:A what:1.7\n", "FeatureNum"),
+        ("1 qid:A 1:what\n", "FeatureValNotFloat"),
+        ("nope qid:A 1:1\n", "Label"),
+        ("nan qid:A 1:1\n", "LabelIsNan"),
+        ("1 qid:A 1:1 1:2\n", "MultipleDefinitions"),
+        ("1 1:1 2:1\n", "Missing qid"),
+    ):
+        with pytest.raises(Exception, match=what):
+            _load_text(fr, tmp_path, text, name="bad.libsvm")
+    with pytest.raises(Exception):
+        fr.CDataset.open_ranksvm(str(tmp_path / "does-not-exist"))
