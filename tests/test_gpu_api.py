@@ -458,3 +458,51 @@ def test_training_schedules_agree(fr, monkeypatch):
         assert results[label][1] == base[1], label
     # and the schedules really differ in how many launches they need
     assert results["lookahead"][2] <= results["default"][2] < results["no_speculation"][2]
+
+
+@pytest.mark.parametrize("method,k", [("SquaredError", 3), ("SquaredError", 16), ("BinaryGiniImpurity", 5),
+                                      ("InformationGain", 4), ("TrueVarianceReduction", 6)])
+def test_random_forest_trainer_matches_the_sort_based_restatement(fr, oracle, method, k):
+    """train_model(random_forest) against oracle/random_forest_oracle.py, which keeps the
+    reference's sort-by-feature formulation (random_forest.rs:211-286): same seed => the same
+    forest, tree for tree (feature ids, thresholds and leaf values bit-identical)."""
+    from oracle import random_forest_oracle as rfo
+
+    X, y, qid = synth(2500, 9, 120, seed=71)
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    ods = oracle_dataset(oracle, X, y, qid)
+    req = _rf_req(fr, num_trees=5, seed=1234, min_leaf_support=7, max_depth=6, split_candidates=k)
+    req.params.split_method = method
+    req.params.feature_sampling_rate, req.params.instance_sampling_rate = 0.5, 0.4
+    got = ds.train_model(req).to_dict()
+    traces = []
+    exp = rfo.learn_forest(ods, {"seed": 1234, "num_trees": 5, "split_method": method, "min_leaf_support": 7,
+                                 "max_depth": 6, "split_candidates": k, "feature_sampling_rate": 0.5,
+                                 "instance_sampling_rate": 0.4}, traces)
+    assert got["Ensemble"]["weights"] == exp["Ensemble"]["weights"]
+    near_ties = nodes = 0
+
+    def walk(a, b, trace, path):
+        # identical trees, except that where two candidate splits of a node tie to within the
+        # rounding of their importance sums -- sums the reference takes in an order it does not
+        # specify (sort_unstable among equal feature values) -- either may be chosen
+        nonlocal near_ties, nodes
+        nodes += 1
+        assert list(a) == list(b), path
+        if "LeafNode" in a:
+            assert a["LeafNode"] == b["LeafNode"], path
+            return
+        fa, fb = a["FeatureSplit"], b["FeatureSplit"]
+        if (fa["fid"], fa["split"]) != (fb["fid"], fb["split"]):
+            cands = {(f, sp): imp for f, sp, imp in trace[path]}
+            assert (fa["fid"], fa["split"]) in cands, (path, fa["fid"], fa["split"])
+            ia, ib = cands[(fa["fid"], fa["split"])], cands[(fb["fid"], fb["split"])]
+            assert abs(ia - ib) <= 1e-9 * max(1.0, abs(ib)), (path, ia, ib)
+            near_ties += 1
+            return
+        walk(fa["lhs"], fb["lhs"], trace, path + "L")
+        walk(fa["rhs"], fb["rhs"], trace, path + "R")
+
+    for ma, mb, trace in zip(got["Ensemble"]["models"], exp["Ensemble"]["models"], traces):
+        walk(ma["DecisionTree"], mb["DecisionTree"], trace, "")
+    assert nodes > 50 and near_ties <= 2

@@ -173,3 +173,21 @@ def test_ca_improves_and_is_deterministic(oracle, trec_train):
     assert a["score"] >= 0.43
     per_query = oracle.evaluate_scores(trec_train, oracle.score_linear(trec_train.X, a["weights"]), "ndcg@5")
     assert oracle.mean(per_query) == a["score"]
+
+
+def test_oracle_forest_trainer_reproduces_the_regression_tree_known_answer(oracle, goldens):
+    # random_forest.rs:465-506 with the sort-based restatement (oracle/random_forest_oracle.py):
+    # the learned tree must fit ys exactly, through the splits SURVEY 8c derived (6.25, 3.03125)
+    from oracle import random_forest_oracle as rfo
+
+    g = goldens["regression_tree"]
+    X = np.asarray(g["xs"], dtype=np.float32).reshape(-1, 1)
+    ys = np.asarray(g["ys"], dtype=np.float32)
+    ds = oracle.OracleDataset(X, ys, ["query"] * len(ys))
+    m = rfo.learn_forest(ds, {"seed": 42, "num_trees": 1, "split_method": "SquaredError", "min_leaf_support": 1,
+                              "max_depth": 10, "split_candidates": 32, "feature_sampling_rate": 0.25,
+                              "instance_sampling_rate": 0.5})
+    tree = m["Ensemble"]["models"][0]["DecisionTree"]
+    assert tree["FeatureSplit"]["split"] == 6.25
+    assert tree["FeatureSplit"]["lhs"]["FeatureSplit"]["split"] == 3.03125
+    assert oracle.score_model(X, m).tolist() == [float(v) for v in ys]
