@@ -23,7 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CU_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-ffp-contract=off"]
 
-CU_SOURCES = ["device.cu", "sweep_fast.cu", "trees.cu", "long_queries.cu"]
+CU_SOURCES = ["device.cu", "sweep_fast.cu", "trees.cu", "long_queries.cu", "rf_induction.cu"]
 CXX_SOURCES = ["dataset.cpp", "model.cpp", "evaluator.cpp", "coordinate_ascent.cpp",
                "random_forest.cpp", "training.cpp", "capi.cpp"]
 

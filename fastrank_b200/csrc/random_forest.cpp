@@ -1,6 +1,6 @@
 // random_forest.cpp -- random-forest learner (random_forest.rs:14-408) on the host.
 //
-// Tree INDUCTION is host work (per node: feature statistics, then per feature the partition
+// Tree INDUCTION decisions are host work (per node: feature statistics, then per feature the partition
 // statistics of k-1 evenly spaced thresholds; SURVEY.md 2 row 5 keeps it off the GPU path); what
 // the forest produces -- a WeightedEnsemble of regression
 // trees -- is scored and evaluated on the GPU (device.cu model_score_kernel + scores_eval_kernel):
@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <mutex>
 #include <thread>
 
 #include "host.hpp"
@@ -260,6 +261,180 @@ std::unique_ptr<TreeNode> learn_recursive(const Ctx &c, const std::vector<uint32
     return node;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// The same learner with the per-level statistics produced on the GPU (rf_induction.cu,
+// SURVEY.md 8f.2).  The decisions are the host's: stop rules (random_forest.rs:369-378),
+// threshold de-duplication and leaf-size test (:236-259), importance (:90-125), "last maximal"
+// among candidates (:270, :395).  Sums are integers (labels in units of 2^-FR_RF_GAIN_BITS), so a
+// forest does not depend on the order in which the device adds; the squared error of a side is
+// sq - sum^2 / n from those exact integers where the two-pass host code sums (mean - y)^2 -- the
+// same number up to its last bits, which can only matter between candidates that tie to ~1e-15.
+// ---------------------------------------------------------------------------------------
+struct TooManyNodes {};
+
+double side_importance(const std::string &method, uint64_t n, uint64_t positive, int64_t sum, int64_t sq,
+                       bool *degenerate) {
+    if (n == 0) return 0.0;
+    if (method == "BinaryGiniImpurity" || method == "InformationGain") {
+        const double cnt = (double)n;
+        const double p_yes = (double)positive / cnt, p_no = (cnt - (double)positive) / cnt;
+        if (method == "BinaryGiniImpurity") return (p_yes * (1.0 - p_yes) + p_no * (1.0 - p_no)) * cnt;
+        return (-plogp(p_yes) - plogp(p_no)) * cnt;
+    }
+    const __int128 num = (__int128)n * (__int128)sq - (__int128)sum * (__int128)sum;  // n * SSE, exact
+    const double scale = (double)(1ull << (2 * FR_RF_GAIN_BITS));
+    const double sse = (double)num / ((double)n * scale);
+    if (method == "SquaredError") return sse;
+    if (n < 2) {  // label_stats(..).unwrap() of a single instance
+        *degenerate = true;
+        return 0.0;
+    }
+    return sse / (double)(n - 1) * (double)n;  // variance * weight
+}
+
+std::unique_ptr<TreeNode> learn_tree_device(const Ctx &c, fr_dev_rf *rf, const std::vector<uint32_t> &features,
+                                            const std::vector<uint32_t> &instances) {
+    const RandomForestParams &p = c.p;
+    auto mean_of = [](int64_t sum, uint64_t n) {
+        return n ? (double)sum / (double)(1ull << FR_RF_GAIN_BITS) / (double)n : 0.0;
+    };
+    // the root's stop rules need no statistics (:369-378)
+    if (features.empty() || instances.empty() || 1 >= p.max_depth || instances.size() < (size_t)p.min_leaf_support)
+        return leaf(compute_output(c, instances.data(), instances.size()));
+    if (fr_dev_rf_begin_tree(rf, instances.data(), instances.size(), features.data(), features.size()))
+        throw Error(fr_dev_last_error());
+    struct Active {
+        std::unique_ptr<TreeNode> *slot;
+        uint32_t depth;
+    };
+    std::unique_ptr<TreeNode> root;
+    std::vector<Active> active{{&root, 1u}};
+    const uint32_t k = p.split_candidates;
+    const size_t F = features.size();
+    std::vector<uint64_t> node_n;
+    std::vector<int64_t> node_sum, b_sum, b_sq;
+    std::vector<float> gmin, gmax, fmin, fmax;
+    std::vector<uint32_t> b_n, b_pos, t_fid;
+    std::vector<double> t_split;
+    std::vector<int32_t> t_left, t_right;
+    while (!active.empty()) {
+        const uint32_t na = (uint32_t)active.size();
+        if (na > 1024) throw TooManyNodes();
+        node_n.assign(na, 0);
+        node_sum.assign(na, 0);
+        gmin.assign(na, 0.f);
+        gmax.assign(na, 0.f);
+        fmin.assign((size_t)na * F, 0.f);
+        fmax.assign((size_t)na * F, 0.f);
+        b_n.assign((size_t)na * F * k, 0);
+        b_pos.assign((size_t)na * F * k, 0);
+        b_sum.assign((size_t)na * F * k, 0);
+        b_sq.assign((size_t)na * F * k, 0);
+        if (fr_dev_rf_level_stats(rf, na, k, node_n.data(), node_sum.data(), gmin.data(), gmax.data(), fmin.data(),
+                                  fmax.data(), b_n.data(), b_pos.data(), b_sum.data(), b_sq.data()))
+            throw Error(fr_dev_last_error());
+        t_fid.assign(na, 0xffffffffu);
+        t_split.assign(na, 0.0);
+        t_left.assign(na, -1);
+        t_right.assign(na, -1);
+        std::vector<Active> next;
+        for (uint32_t a = 0; a < na; ++a) {
+            const uint64_t n = node_n[a];
+            bool have = false;
+            double best_imp = 0.0, best_split = 0.0;
+            uint32_t best_f = 0;
+            uint64_t best_nl = 0, best_posl = 0;
+            int64_t best_suml = 0;
+            // label_stats (:217-221) and FeatureStats.finish() both need more than one instance
+            if (n > 1 && gmax[a] != gmin[a]) {
+                for (size_t fa = 0; fa < F; ++fa) {
+                    const double lo = (double)fmin[(size_t)a * F + fa];
+                    const double range = (double)fmax[(size_t)a * F + fa] - lo;
+                    const size_t base = ((size_t)a * F + fa) * k;
+                    uint64_t tot_pos = 0;
+                    int64_t tot_sum = 0, tot_sq = 0;
+                    for (uint32_t b = 0; b < k; ++b) {
+                        tot_pos += b_pos[base + b];
+                        tot_sum += b_sum[base + b];
+                        tot_sq += b_sq[base + b];
+                    }
+                    uint64_t nl = 0, posl = 0, prev = 0;
+                    int64_t suml = 0, sql = 0;
+                    bool have_prev = false, cand_have = false;
+                    double cand_imp = 0.0, cand_split = 0.0;
+                    uint64_t cand_nl = 0, cand_posl = 0;
+                    int64_t cand_suml = 0;
+                    for (uint32_t i = 1; i < k; ++i) {
+                        nl += b_n[base + i - 1];
+                        posl += b_pos[base + i - 1];
+                        suml += b_sum[base + i - 1];
+                        sql += b_sq[base + i - 1];
+                        if (have_prev && prev == nl) continue;
+                        have_prev = true;
+                        prev = nl;
+                        const uint64_t nr = n - nl;
+                        if (nl < p.min_leaf_support || nr < p.min_leaf_support) continue;
+                        bool degenerate = false;
+                        const double imp = -(side_importance(p.split_method, nl, posl, suml, sql, &degenerate) +
+                                             side_importance(p.split_method, nr, tot_pos - posl, tot_sum - suml,
+                                                             tot_sq - sql, &degenerate));
+                        if (degenerate)
+                            throw Error("TrueVarianceReduction needs at least two instances on each side of a split");
+                        if (imp != imp) throw Error("split importance is NaN");
+                        if (!cand_have || imp >= cand_imp) {
+                            cand_have = true;
+                            cand_imp = imp;
+                            cand_split = ((double)i / (double)k) * range + lo;
+                            cand_nl = nl;
+                            cand_posl = posl;
+                            cand_suml = suml;
+                        }
+                    }
+                    if (cand_have && (!have || cand_imp >= best_imp)) {
+                        have = true;
+                        best_imp = cand_imp;
+                        best_split = cand_split;
+                        best_f = (uint32_t)fa;
+                        best_nl = cand_nl;
+                        best_posl = cand_posl;
+                        best_suml = cand_suml;
+                    }
+                }
+            }
+            (void)best_posl;
+            if (!have) {  // NoFeatureSplitCandidates: the parent turns this node into a leaf
+                *active[a].slot = leaf(mean_of(node_sum[a], n));
+                continue;
+            }
+            std::unique_ptr<TreeNode> node(new TreeNode());
+            node->leaf = false;
+            node->fid = features[best_f];
+            node->split = best_split;
+            TreeNode *raw = node.get();
+            *active[a].slot = std::move(node);
+            t_fid[a] = features[best_f];
+            t_split[a] = best_split;
+            const uint32_t child_depth = active[a].depth + 1;
+            auto child = [&](std::unique_ptr<TreeNode> *slot, uint64_t cn, int64_t csum, int32_t *id_out) {
+                if (cn == 0 || child_depth >= p.max_depth || cn < p.min_leaf_support) {
+                    *slot = leaf(mean_of(csum, cn));  // the recursion would return Err here
+                    *id_out = -1;
+                } else {
+                    *id_out = (int32_t)next.size();
+                    next.push_back({slot, child_depth});
+                }
+            };
+            child(&raw->lhs, best_nl, best_suml, &t_left[a]);
+            child(&raw->rhs, n - best_nl, node_sum[a] - best_suml, &t_right[a]);
+        }
+        if (fr_dev_rf_partition(rf, na, t_fid.data(), t_split.data(), t_left.data(), t_right.data()))
+            throw Error(fr_dev_last_error());
+        active.swap(next);
+    }
+    return root;
+}
+
 uint32_t tree_depth(const TreeNode &n) {  // random_forest.rs:159-166
     return n.leaf ? 1u : 1u + std::max(tree_depth(*n.lhs), tree_depth(*n.rhs));
 }
@@ -295,6 +470,30 @@ Model random_forest_learn(const RandomForestParams &p, const DatasetView &view, 
     });
     if (all_features.empty()) throw Error("dataset has no features");
 
+    // Where do the per-level statistics come from?  The device path needs a dense source (no
+    // missing values) and labels that are exact in its integer unit; FASTRANK_RF=host / gpu
+    // overrides the size heuristic.
+    bool on_device = parent.dense_source && view.num_instances() >= 50000;
+    if (const char *env = getenv("FASTRANK_RF")) {
+        if (std::string(env) == "host") on_device = false;
+        if (std::string(env) == "gpu") on_device = parent.dense_source;
+    }
+    if (on_device) {
+        const double unit = (double)(1 << FR_RF_GAIN_BITS);
+        for (size_t i = 0; i < parent.n && on_device; ++i) {
+            const double g = (double)parent.gains[i] * unit;
+            if (g != std::floor(g) || std::fabs((double)parent.gains[i]) > 16.0) on_device = false;
+        }
+    }
+    struct RfHandle {
+        fr_dev_rf *p = nullptr;
+        ~RfHandle() {
+            if (p) fr_dev_rf_destroy(p);
+        }
+    } rf;
+    if (on_device && fr_dev_rf_create(view.parent->device(), &rf.p)) throw Error(fr_dev_last_error());
+    std::mutex device_mu;  // one tree at a time drives the device state
+
     std::vector<std::unique_ptr<TreeNode>> trees(p.num_trees);
     std::vector<std::string> failures(p.num_trees);
     std::atomic<uint32_t> next{0};
@@ -316,8 +515,20 @@ Model random_forest_learn(const RandomForestParams &p, const DatasetView &view, 
                 std::vector<uint32_t> instances;
                 for (size_t g = 0; g < groups.size(); ++g)
                     if (keep[g]) instances.insert(instances.end(), groups[g].second.begin(), groups[g].second.end());
-                std::unique_ptr<TreeNode> root = learn_recursive(ctx, features, instances, 1);
-                if (!root) root = leaf(compute_output(ctx, instances.data(), instances.size()));  // :344-352
+                std::unique_ptr<TreeNode> root;
+                bool done = false;
+                if (rf.p) {
+                    std::lock_guard<std::mutex> lock(device_mu);
+                    try {
+                        root = learn_tree_device(ctx, rf.p, features, instances);
+                        done = true;
+                    } catch (const TooManyNodes &) {  // more than 1024 open nodes on a level: host path
+                    }
+                }
+                if (!done) {
+                    root = learn_recursive(ctx, features, instances, 1);
+                    if (!root) root = leaf(compute_output(ctx, instances.data(), instances.size()));  // :344-352
+                }
                 trees[idx] = std::move(root);
             } catch (const std::exception &e) {
                 failures[idx] = e.what();
@@ -326,7 +537,9 @@ Model random_forest_learn(const RandomForestParams &p, const DatasetView &view, 
     };
     {
         unsigned hw = std::thread::hardware_concurrency();
-        const unsigned nthreads = std::max(1u, std::min<unsigned>(hw ? hw : 1u, p.num_trees));
+        // sampling runs on the pool either way; with the device path the tree growth itself is
+        // serialised on the GPU, so a few threads are enough to keep it fed
+        const unsigned nthreads = std::max(1u, std::min<unsigned>(rf.p ? 4u : (hw ? hw : 1u), p.num_trees));
         std::vector<std::thread> pool;
         for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
         worker();

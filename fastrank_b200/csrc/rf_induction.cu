@@ -1,0 +1,358 @@
+// rf_induction.cu -- random-forest tree induction statistics on the device.
+//
+// The reference grows a tree node by node (random_forest.rs:362-408): per node FeatureStats
+// (normalizers.rs:13-36: min / max per feature), then per feature k-1 evenly spaced thresholds
+// between min and max, each scored from the labels on its two sides (:211-286).  Here a tree
+// grows LEVEL by level; the instances sampled for the tree carry the id of the node they sit in,
+// and two passes over (instance, feature) pairs produce, for every active node at once,
+//   pass 1   min / max of every sampled feature, and the node's label statistics
+//   pass 2   per (node, feature, bucket between consecutive thresholds): count, positives,
+//            sum and sum of squares of the labels
+// from which the host scores every candidate split (prefix sums over buckets) exactly as the
+// reference defines them, picks the winners and sends back a partition table.  Label sums are
+// integers (labels in units of 2^-12), so the statistics -- and the forest -- do not depend on
+// the order in which threads add.  X is read feature-major from the resident matrix: threads of
+// a warp read consecutive positions of one feature row.
+#include "device_common.cuh"
+
+namespace {
+
+constexpr int kChunk = 2048;   // sampled instances per CTA
+constexpr int kRfThreads = 256;
+constexpr double kGainScale = 4096.0;  // labels are accumulated in units of 2^-12 (FR_RF_GAIN_BITS)
+
+__device__ __forceinline__ int ford(float v) {  // order-preserving float -> int
+    const int i = __float_as_int(v);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float fdro(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+struct RfLevel {
+    const float *x;
+    size_t ld;
+    const float *gain;        // by position
+    const uint32_t *samp_pos; // [m] position of every sampled instance
+    const int *node_of;       // [m] active node of the instance, -1 = settled in a leaf
+    uint32_t m;
+    const uint32_t *feats;    // [F]
+    uint32_t F, n_active, k;
+    int *fmin, *fmax;                 // [n_active][F] ordered-int min / max
+    unsigned long long *node_n;       // [n_active]
+    long long *node_sum;              // [n_active] labels, 2^-12 units
+    int *gmin, *gmax;                 // [n_active] ordered-int label min / max
+    unsigned *b_n, *b_pos;            // [n_active][F][k]
+    long long *b_sum, *b_sq;          // [n_active][F][k]  2^-12 and 2^-24 units
+};
+
+// pass 1: grid (chunks, F)
+__global__ void __launch_bounds__(kRfThreads) rf_minmax_kernel(RfLevel L) {
+    extern __shared__ int sm[];
+    int *smn = sm, *smx = sm + L.n_active;
+    const uint32_t f = blockIdx.y;
+    const bool labels = f == 0;
+    int *sgmn = smx + L.n_active, *sgmx = sgmn + L.n_active;
+    unsigned *scnt = (unsigned *)(sgmx + L.n_active);
+    long long *ssum = (long long *)(scnt + L.n_active + (L.n_active & 1));
+    for (uint32_t a = threadIdx.x; a < L.n_active; a += blockDim.x) {
+        smn[a] = INT_MAX;
+        smx[a] = INT_MIN;
+        if (labels) {
+            sgmn[a] = INT_MAX;
+            sgmx[a] = INT_MIN;
+            scnt[a] = 0u;
+            ssum[a] = 0ll;
+        }
+    }
+    __syncthreads();
+    const float *__restrict__ row = L.x + (size_t)L.feats[f] * L.ld;
+    const uint32_t i0 = blockIdx.x * kChunk, i1 = min(L.m, i0 + kChunk);
+    for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const int nid = L.node_of[i];
+        if (nid < 0) continue;
+        const uint32_t p = L.samp_pos[i];
+        const int o = ford(__ldg(row + p));
+        atomicMin(&smn[nid], o);
+        atomicMax(&smx[nid], o);
+        if (labels) {
+            const float g = __ldg(L.gain + p);
+            atomicMin(&sgmn[nid], ford(g));
+            atomicMax(&sgmx[nid], ford(g));
+            atomicAdd(&scnt[nid], 1u);
+            atomicAdd((unsigned long long *)&ssum[nid], (unsigned long long)__double2ll_rn((double)g * kGainScale));
+        }
+    }
+    __syncthreads();
+    for (uint32_t a = threadIdx.x; a < L.n_active; a += blockDim.x) {
+        if (smn[a] != INT_MAX) {
+            atomicMin(&L.fmin[(size_t)a * L.F + f], smn[a]);
+            atomicMax(&L.fmax[(size_t)a * L.F + f], smx[a]);
+        }
+        if (labels && scnt[a]) {
+            atomicMin(&L.gmin[a], sgmn[a]);
+            atomicMax(&L.gmax[a], sgmx[a]);
+            atomicAdd(&L.node_n[a], (unsigned long long)scnt[a]);
+            atomicAdd((unsigned long long *)&L.node_sum[a], (unsigned long long)ssum[a]);
+        }
+    }
+}
+
+// pass 2: grid (chunks, F).  Bucket b of a value = number of thresholds it is not below, i.e. the
+// first i (1-based) with v < i/k * range + min is bucket i-1; values above every threshold fall in
+// bucket k-1.  The threshold expression is random_forest.rs:231-234, evaluated in f64 with a
+// separate multiply and add, as on the host.
+template <bool SMEM>
+__global__ void __launch_bounds__(kRfThreads) rf_bucket_kernel(RfLevel L) {
+    extern __shared__ long long sm64[];
+    const uint32_t f = blockIdx.y, k = L.k;
+    const size_t cells = (size_t)L.n_active * k;
+    long long *ssum = sm64, *ssq = sm64 + cells;
+    unsigned *sn = (unsigned *)(ssq + cells), *spos = sn + cells;
+    if (SMEM) {
+        for (size_t c = threadIdx.x; c < cells; c += blockDim.x) {
+            ssum[c] = 0;
+            ssq[c] = 0;
+            sn[c] = 0;
+            spos[c] = 0;
+        }
+        __syncthreads();
+    }
+    const float *__restrict__ row = L.x + (size_t)L.feats[f] * L.ld;
+    const uint32_t i0 = blockIdx.x * kChunk, i1 = min(L.m, i0 + kChunk);
+    for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const int nid = L.node_of[i];
+        if (nid < 0) continue;
+        const uint32_t p = L.samp_pos[i];
+        const double v = (double)__ldg(row + p);
+        const double lo = (double)fdro(L.fmin[(size_t)nid * L.F + f]);
+        const double range = __dsub_rn((double)fdro(L.fmax[(size_t)nid * L.F + f]), lo);
+        uint32_t b = 0;
+        while (b + 1 < k) {
+            const double pos = __dadd_rn(__dmul_rn((double)(b + 1) / (double)k, range), lo);
+            if (v < pos) break;
+            ++b;
+        }
+        const float g = __ldg(L.gain + p);
+        const long long y = __double2ll_rn((double)g * kGainScale);
+        const size_t cell = (size_t)nid * k + b;
+        if (SMEM) {
+            atomicAdd(&sn[cell], 1u);
+            if (g > 0.0f) atomicAdd(&spos[cell], 1u);
+            atomicAdd((unsigned long long *)&ssum[cell], (unsigned long long)y);
+            atomicAdd((unsigned long long *)&ssq[cell], (unsigned long long)(y * y));
+        } else {
+            const size_t gc = ((size_t)nid * L.F + f) * k + b;
+            atomicAdd(&L.b_n[gc], 1u);
+            if (g > 0.0f) atomicAdd(&L.b_pos[gc], 1u);
+            atomicAdd((unsigned long long *)&L.b_sum[gc], (unsigned long long)y);
+            atomicAdd((unsigned long long *)&L.b_sq[gc], (unsigned long long)(y * y));
+        }
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (size_t c = threadIdx.x; c < cells; c += blockDim.x) {
+            if (!sn[c]) continue;
+            const size_t nid = c / k, b = c % k;
+            const size_t gc = (nid * L.F + f) * k + b;
+            atomicAdd(&L.b_n[gc], sn[c]);
+            if (spos[c]) atomicAdd(&L.b_pos[gc], spos[c]);
+            atomicAdd((unsigned long long *)&L.b_sum[gc], (unsigned long long)ssum[c]);
+            atomicAdd((unsigned long long *)&L.b_sq[gc], (unsigned long long)ssq[c]);
+        }
+    }
+}
+
+// apply the host's decisions: every instance of a split node moves to its child
+__global__ void rf_partition_kernel(const float *__restrict__ x, size_t ld, const uint32_t *__restrict__ samp_pos,
+                                    int *__restrict__ node_of, uint32_t m, const uint32_t *__restrict__ fid,
+                                    const double *__restrict__ split, const int *__restrict__ left,
+                                    const int *__restrict__ right) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int nid = node_of[i];
+    if (nid < 0) return;
+    const uint32_t f = fid[nid];
+    if (f == 0xffffffffu) {
+        node_of[i] = -1;
+        return;
+    }
+    const double v = (double)__ldg(x + (size_t)f * ld + samp_pos[i]);
+    node_of[i] = v < split[nid] ? left[nid] : right[nid];  // lhs = values below the threshold
+}
+
+}  // namespace
+
+struct fr_dev_rf {
+    fr_dev_dataset *ds = nullptr;
+    cudaStream_t stream = nullptr;
+    uint32_t m = 0, F = 0;
+    DevBuf<uint32_t> samp_pos, feats, t_fid;
+    DevBuf<int> node_of, t_left, t_right;
+    DevBuf<double> t_split;
+    DevBuf<unsigned char> stats;  // one blob per level, cleared and read back in one go
+    ~fr_dev_rf() {
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+extern "C" {
+
+int fr_dev_rf_create(fr_dev_dataset *ds, fr_dev_rf **out) {
+    if (!ds || !out) return fail("fr_dev_rf_create: NULL argument");
+    CU(cudaSetDevice(ds->device));
+    std::unique_ptr<fr_dev_rf> rf(new fr_dev_rf());
+    rf->ds = ds;
+    CU(cudaStreamCreateWithFlags(&rf->stream, cudaStreamNonBlocking));
+    *out = rf.release();
+    return 0;
+}
+
+void fr_dev_rf_destroy(fr_dev_rf *rf) {
+    if (!rf) return;
+    cudaSetDevice(rf->ds->device);
+    delete rf;
+}
+
+int fr_dev_rf_begin_tree(fr_dev_rf *rf, const uint32_t *instances, size_t m, const uint32_t *features,
+                         size_t n_features) {
+    if (!rf || (!instances && m) || !features || n_features == 0) return fail("fr_dev_rf_begin_tree: bad argument");
+    fr_dev_dataset *ds = rf->ds;
+    CU(cudaSetDevice(ds->device));
+    std::vector<uint32_t> pos(m);
+    for (size_t i = 0; i < m; ++i) {
+        if (instances[i] >= ds->n) return fail("fr_dev_rf_begin_tree: instance id out of range");
+        pos[i] = ds->pos_of_inst[instances[i]];
+    }
+    for (size_t a = 0; a < n_features; ++a)
+        if (features[a] >= ds->d) return fail("fr_dev_rf_begin_tree: feature id out of range");
+    rf->m = (uint32_t)m;
+    rf->F = (uint32_t)n_features;
+    CU(rf->samp_pos.ensure(std::max<size_t>(m, 1)));
+    CU(rf->node_of.ensure(std::max<size_t>(m, 1)));
+    CU(rf->feats.ensure(n_features));
+    if (m) CU(cudaMemcpyAsync(rf->samp_pos.p, pos.data(), sizeof(uint32_t) * m, cudaMemcpyHostToDevice, rf->stream));
+    CU(cudaMemcpyAsync(rf->feats.p, features, sizeof(uint32_t) * n_features, cudaMemcpyHostToDevice, rf->stream));
+    CU(cudaMemsetAsync(rf->node_of.p, 0, sizeof(int) * std::max<size_t>(m, 1), rf->stream));  // everyone in the root
+    CU(cudaStreamSynchronize(rf->stream));  // `pos` is a local
+    return 0;
+}
+
+int fr_dev_rf_level_stats(fr_dev_rf *rf, uint32_t n_active, uint32_t k, uint64_t *node_n, int64_t *node_sum,
+                          float *gmin, float *gmax, float *fmin, float *fmax, uint32_t *b_n, uint32_t *b_pos,
+                          int64_t *b_sum, int64_t *b_sq) {
+    if (!rf || n_active == 0 || k < 2) return fail("fr_dev_rf_level_stats: bad argument");
+    fr_dev_dataset *ds = rf->ds;
+    CU(cudaSetDevice(ds->device));
+    cudaStream_t s = rf->stream;
+    const size_t nf = (size_t)n_active * rf->F, cells = nf * k;
+    // blob: [node_n u64][node_sum i64][b_sum i64][b_sq i64][fmin i32][fmax i32][gmin][gmax][b_n u32][b_pos u32]
+    const size_t o_node_n = 0, o_node_sum = o_node_n + 8 * (size_t)n_active, o_bsum = o_node_sum + 8 * (size_t)n_active,
+                 o_bsq = o_bsum + 8 * cells, o_fmin = o_bsq + 8 * cells, o_fmax = o_fmin + 4 * nf,
+                 o_gmin = o_fmax + 4 * nf, o_gmax = o_gmin + 4 * (size_t)n_active, o_bn = o_gmax + 4 * (size_t)n_active,
+                 o_bpos = o_bn + 4 * cells, total = o_bpos + 4 * cells;
+    CU(rf->stats.ensure(total));
+    unsigned char *b = rf->stats.p;
+    CU(cudaMemsetAsync(b, 0, total, s));
+    // min slots start at INT_MAX, max slots at INT_MIN
+    {
+        std::vector<int> init(2 * nf + 2 * (size_t)n_active);
+        std::fill(init.begin(), init.begin() + nf, INT_MAX);
+        std::fill(init.begin() + nf, init.begin() + 2 * nf, INT_MIN);
+        std::fill(init.begin() + 2 * nf, init.begin() + 2 * nf + n_active, INT_MAX);
+        std::fill(init.begin() + 2 * nf + n_active, init.end(), INT_MIN);
+        CU(cudaMemcpyAsync(b + o_fmin, init.data(), sizeof(int) * init.size(), cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    RfLevel L;
+    L.x = ds->x.p;
+    L.ld = ds->ld;
+    L.gain = ds->gain.p;
+    L.samp_pos = rf->samp_pos.p;
+    L.node_of = rf->node_of.p;
+    L.m = rf->m;
+    L.feats = rf->feats.p;
+    L.F = rf->F;
+    L.n_active = n_active;
+    L.k = k;
+    L.node_n = (unsigned long long *)(b + o_node_n);
+    L.node_sum = (long long *)(b + o_node_sum);
+    L.b_sum = (long long *)(b + o_bsum);
+    L.b_sq = (long long *)(b + o_bsq);
+    L.fmin = (int *)(b + o_fmin);
+    L.fmax = (int *)(b + o_fmax);
+    L.gmin = (int *)(b + o_gmin);
+    L.gmax = (int *)(b + o_gmax);
+    L.b_n = (unsigned *)(b + o_bn);
+    L.b_pos = (unsigned *)(b + o_bpos);
+    const dim3 grid((rf->m + kChunk - 1) / kChunk, rf->F);
+    if (rf->m > 0) {
+        const size_t smem1 = sizeof(int) * 4 * (size_t)n_active + sizeof(unsigned) * ((size_t)n_active + 1) +
+                             sizeof(long long) * (size_t)n_active + 16;
+        if (smem1 > 200 * 1024) return fail("fr_dev_rf_level_stats: too many active nodes");
+        if (smem1 > 48 * 1024)
+            CU(cudaFuncSetAttribute(rf_minmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        rf_minmax_kernel<<<grid, kRfThreads, smem1, s>>>(L);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        const size_t smem2 = (size_t)n_active * k * 24;
+        if (smem2 <= 96 * 1024) {
+            if (smem2 > 48 * 1024)
+                CU(cudaFuncSetAttribute(rf_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            rf_bucket_kernel<true><<<grid, kRfThreads, smem2, s>>>(L);
+        } else {
+            rf_bucket_kernel<false><<<grid, kRfThreads, 0, s>>>(L);
+        }
+        LAUNCHED();
+        CU(cudaGetLastError());
+    }
+    std::vector<unsigned char> host(total);
+    CU(cudaMemcpyAsync(host.data(), b, total, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(node_n, host.data() + o_node_n, 8 * (size_t)n_active);
+    memcpy(node_sum, host.data() + o_node_sum, 8 * (size_t)n_active);
+    memcpy(b_sum, host.data() + o_bsum, 8 * cells);
+    memcpy(b_sq, host.data() + o_bsq, 8 * cells);
+    memcpy(b_n, host.data() + o_bn, 4 * cells);
+    memcpy(b_pos, host.data() + o_bpos, 4 * cells);
+    auto unord = [](int i) {
+        const int j = i >= 0 ? i : i ^ 0x7fffffff;
+        float f;
+        memcpy(&f, &j, 4);
+        return f;
+    };
+    const int *hfmin = (const int *)(host.data() + o_fmin), *hfmax = (const int *)(host.data() + o_fmax);
+    const int *hgmin = (const int *)(host.data() + o_gmin), *hgmax = (const int *)(host.data() + o_gmax);
+    for (size_t i = 0; i < nf; ++i) {
+        fmin[i] = unord(hfmin[i]);
+        fmax[i] = unord(hfmax[i]);
+    }
+    for (uint32_t a = 0; a < n_active; ++a) {
+        gmin[a] = unord(hgmin[a]);
+        gmax[a] = unord(hgmax[a]);
+    }
+    return 0;
+}
+
+int fr_dev_rf_partition(fr_dev_rf *rf, uint32_t n_active, const uint32_t *fid, const double *split,
+                        const int32_t *left, const int32_t *right) {
+    if (!rf || !fid || !split || !left || !right) return fail("fr_dev_rf_partition: NULL argument");
+    fr_dev_dataset *ds = rf->ds;
+    CU(cudaSetDevice(ds->device));
+    cudaStream_t s = rf->stream;
+    if (rf->m == 0 || n_active == 0) return 0;
+    CU(rf->t_fid.ensure(n_active));
+    CU(rf->t_split.ensure(n_active));
+    CU(rf->t_left.ensure(n_active));
+    CU(rf->t_right.ensure(n_active));
+    CU(cudaMemcpyAsync(rf->t_fid.p, fid, sizeof(uint32_t) * n_active, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(rf->t_split.p, split, sizeof(double) * n_active, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(rf->t_left.p, left, sizeof(int) * n_active, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(rf->t_right.p, right, sizeof(int) * n_active, cudaMemcpyHostToDevice, s));
+    rf_partition_kernel<<<(rf->m + 255) / 256, 256, 0, s>>>(ds->x.p, ds->ld, rf->samp_pos.p, rf->node_of.p, rf->m,
+                                                           rf->t_fid.p, rf->t_split.p, rf->t_left.p, rf->t_right.p);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // extern "C"

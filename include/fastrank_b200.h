@@ -204,6 +204,39 @@ int fr_dev_score_model(fr_dev_dataset *ds, const fr_dev_model *m, double *out_sc
 int fr_dev_eval_model(fr_dev_plan *plan, const fr_dev_model *m, int64_t *out_sum_fx,
                       double *out_per_query);
 
+/* --------------------------------------------------------------------------------------
+ * Random-forest induction statistics (random_forest.rs:211-286, :362-408; normalizers.rs:13-36),
+ * one tree at a time, level by level.  The host keeps the reference's decision logic; the device
+ * produces, for all active nodes of a level at once, what those decisions need.
+ * Label sums are integers in units of 2^-FR_RF_GAIN_BITS (and their squares), so they do not
+ * depend on the order of accumulation; the caller guarantees every label is a multiple of that
+ * unit with magnitude <= 16.
+ * ------------------------------------------------------------------------------------ */
+#define FR_RF_GAIN_BITS 12
+typedef struct fr_dev_rf fr_dev_rf;
+int fr_dev_rf_create(fr_dev_dataset *ds, fr_dev_rf **out);
+void fr_dev_rf_destroy(fr_dev_rf *rf);
+/* A new tree over `m` sampled instance ids and `n_features` sampled feature ids; every instance
+ * starts in active node 0 (the root). */
+int fr_dev_rf_begin_tree(fr_dev_rf *rf, const uint32_t *instances, size_t m, const uint32_t *features,
+                         size_t n_features);
+/* Statistics of the current level, n_active nodes, k = split_candidates.  Outputs (host):
+ *   node_n, node_sum [n_active]            instances and label sum of the node
+ *   gmin, gmax [n_active]                  label range (label_stats, random_forest.rs:22-31)
+ *   fmin, fmax [n_active][n_features]      FeatureStats min / max
+ *   b_n, b_pos, b_sum, b_sq [n_active][n_features][k]
+ *        per bucket between consecutive thresholds i/k * (max - min) + min, i = 1..k-1
+ *        (bucket b holds the values v with threshold_b <= v < threshold_{b+1}):
+ *        instances, instances with label > 0, label sum, sum of squared labels */
+int fr_dev_rf_level_stats(fr_dev_rf *rf, uint32_t n_active, uint32_t k, uint64_t *node_n, int64_t *node_sum,
+                          float *gmin, float *gmax, float *fmin, float *fmax, uint32_t *b_n, uint32_t *b_pos,
+                          int64_t *b_sum, int64_t *b_sq);
+/* Per active node: fid (0xffffffff: the node is a leaf) and threshold; instances with
+ * value < split move to node left[.], the others to right[.] (ids of the next level, -1 for a
+ * child that is a leaf already). */
+int fr_dev_rf_partition(fr_dev_rf *rf, uint32_t n_active, const uint32_t *fid, const double *split,
+                        const int32_t *left, const int32_t *right);
+
 /* NCCL bootstrap: rank 0 calls fr_dev_comm_unique_id, ships the 128 bytes to every rank by
  * any means (torch.distributed in fastrank_b200/dist.py), then all ranks call
  * fr_dev_comm_create.  Creation also maps every peer's mailbox through CUDA IPC so that

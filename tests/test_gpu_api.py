@@ -460,14 +460,18 @@ def test_training_schedules_agree(fr, monkeypatch):
     assert results["lookahead"][2] <= results["default"][2] < results["no_speculation"][2]
 
 
+@pytest.mark.parametrize("where", ["host", "gpu"])
 @pytest.mark.parametrize("method,k", [("SquaredError", 3), ("SquaredError", 16), ("BinaryGiniImpurity", 5),
                                       ("InformationGain", 4), ("TrueVarianceReduction", 6)])
-def test_random_forest_trainer_matches_the_sort_based_restatement(fr, oracle, method, k):
+def test_random_forest_trainer_matches_the_sort_based_restatement(fr, oracle, method, k, where, monkeypatch):
     """train_model(random_forest) against oracle/random_forest_oracle.py, which keeps the
     reference's sort-by-feature formulation (random_forest.rs:211-286): same seed => the same
     forest, tree for tree (feature ids, thresholds and leaf values bit-identical)."""
     from oracle import random_forest_oracle as rfo
 
+    # "host": statistics by counting passes on the host; "gpu": per-level statistics from
+    # rf_induction.cu (integer label sums) -- the decisions are the same code either way
+    monkeypatch.setenv("FASTRANK_RF", where)
     X, y, qid = synth(2500, 9, 120, seed=71)
     ds = fr.CDataset.from_numpy(X, y, qid)
     ods = oracle_dataset(oracle, X, y, qid)
@@ -506,3 +510,22 @@ def test_random_forest_trainer_matches_the_sort_based_restatement(fr, oracle, me
     for ma, mb, trace in zip(got["Ensemble"]["models"], exp["Ensemble"]["models"], traces):
         walk(ma["DecisionTree"], mb["DecisionTree"], trace, "")
     assert nodes > 50 and near_ties <= 2
+
+
+def test_device_forest_is_deterministic_and_agrees_with_the_host_trainer(fr, monkeypatch):
+    """Larger data, default parameters: the GPU-assisted trainer must give the same forest on
+    every run (integer sums) and rank like the host trainer's forest (the two may only part
+    where two splits tie to the last bits of their importance)."""
+    X, y, qid = synth(120000, 40, 3600, seed=81)
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    req = _rf_req(fr, num_trees=6, seed=9, min_leaf_support=10, max_depth=8, split_candidates=3)
+    req.measure = "ndcg@10"
+    out = {}
+    for where in ("gpu", "gpu", "host"):
+        monkeypatch.setenv("FASTRANK_RF", where)
+        m = ds.train_model(req)
+        out.setdefault(where, []).append((m.to_dict(), ds.evaluate_mean(m, "ndcg@10")))
+    assert out["gpu"][0][0] == out["gpu"][1][0]
+    assert out["gpu"][0][1] == pytest.approx(out["host"][0][1], abs=2e-3)
+    same = sum(a == b for a, b in zip(out["gpu"][0][0]["Ensemble"]["models"], out["host"][0][0]["Ensemble"]["models"]))
+    assert same >= 4  # identical trees unless a near-tie was broken the other way
