@@ -1,17 +1,25 @@
-// random_forest.cpp -- random-forest learner (random_forest.rs:14-408) on the host.
+// random_forest.cpp -- random-forest learner (random_forest.rs:14-408).
 //
-// Tree INDUCTION decisions are host work (per node: feature statistics, then per feature the partition
-// statistics of k-1 evenly spaced thresholds; SURVEY.md 2 row 5 keeps it off the GPU path); what
-// the forest produces -- a WeightedEnsemble of regression
-// trees -- is scored and evaluated on the GPU (device.cu model_score_kernel + scores_eval_kernel):
-// once per tree when the reference's per-tree evaluate_mean is observable (progress table,
-// weight_trees; random_forest.rs:315-318) and for every later evaluate / predict call.
+// The host owns sampling (sampling.rs:38-66) and every decision of the induction: stop rules,
+// which thresholds survive, importance, which candidate wins.  The statistics those decisions
+// need come from one of two places:
+//   * the GPU (rf_induction.cu): a tree grows level by level and the device
+//     produces min / max and bucketed label sums for all open nodes at once -- the default for
+//     dense datasets of some size with labels that are exact in its integer unit;
+//   * counting passes on host threads (learn_recursive below), e.g. for libsvm data with missing
+//     features or tiny datasets.
+// Either way the k-1 evenly spaced thresholds of a feature are scored from counts and sums, not
+// from the reference's sort: a cut at threshold p puts exactly the instances with value < p on
+// the left, so the partitions are the reference's.  The forest is scored and evaluated on the
+// GPU (trees.cu, device.cu): once per tree when the reference's per-tree evaluate_mean is
+// observable (progress table, weight_trees; random_forest.rs:315-318) and for every later
+// evaluate / predict call.
 //
-// Trees are induced on a thread per tree (the reference uses rayon, random_forest.rs:305); the
-// per-tree seeds are drawn up front from the master generator exactly as the reference does, so
-// the result does not depend on the number of threads.  Where the reference's outcome depends on
-// unspecified order (sort_unstable among equal keys, HashMap iteration) this file picks the
-// deterministic choice: node order for sums, "last maximal element", parent query order.
+// The per-tree seeds are drawn up front from the master generator exactly as the reference does
+// (random_forest.rs:293-296), so the result does not depend on the number of threads.  Where the
+// reference's outcome depends on unspecified order (sort_unstable among equal keys, HashMap
+// iteration) this file picks the deterministic choice: node order for sums, "last maximal
+// element", parent query order.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
