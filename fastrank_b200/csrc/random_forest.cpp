@@ -493,19 +493,26 @@ Model random_forest_learn(const RandomForestParams &p, const DatasetView &view, 
             if (g != std::floor(g) || std::fabs((double)parent.gains[i]) > 16.0) on_device = false;
         }
     }
-    struct RfHandle {
-        fr_dev_rf *p = nullptr;
-        ~RfHandle() {
-            if (p) fr_dev_rf_destroy(p);
+    // one induction state (own stream, own buffers) per worker thread: while one tree's level
+    // statistics are being turned into decisions on the host, other trees keep the GPU busy
+    struct RfHandles {
+        std::vector<fr_dev_rf *> p;
+        ~RfHandles() {
+            for (fr_dev_rf *h : p) fr_dev_rf_destroy(h);
         }
     } rf;
-    if (on_device && fr_dev_rf_create(view.parent->device(), &rf.p)) throw Error(fr_dev_last_error());
-    std::mutex device_mu;  // one tree at a time drives the device state
+    const unsigned device_workers = on_device ? std::min<unsigned>(4u, p.num_trees) : 0u;
+    for (unsigned w = 0; w < device_workers; ++w) {
+        fr_dev_rf *h = nullptr;
+        if (fr_dev_rf_create(view.parent->device(), &h)) throw Error(fr_dev_last_error());
+        rf.p.push_back(h);
+    }
 
     std::vector<std::unique_ptr<TreeNode>> trees(p.num_trees);
     std::vector<std::string> failures(p.num_trees);
     std::atomic<uint32_t> next{0};
-    auto worker = [&]() {
+    auto worker = [&](unsigned worker_id) {
+        fr_dev_rf *my_rf = worker_id < rf.p.size() ? rf.p[worker_id] : nullptr;
         for (;;) {
             const uint32_t idx = next.fetch_add(1);
             if (idx >= p.num_trees) return;
@@ -525,10 +532,9 @@ Model random_forest_learn(const RandomForestParams &p, const DatasetView &view, 
                     if (keep[g]) instances.insert(instances.end(), groups[g].second.begin(), groups[g].second.end());
                 std::unique_ptr<TreeNode> root;
                 bool done = false;
-                if (rf.p) {
-                    std::lock_guard<std::mutex> lock(device_mu);
+                if (my_rf) {
                     try {
-                        root = learn_tree_device(ctx, rf.p, features, instances);
+                        root = learn_tree_device(ctx, my_rf, features, instances);
                         done = true;
                     } catch (const TooManyNodes &) {  // more than 1024 open nodes on a level: host path
                     }
@@ -545,12 +551,11 @@ Model random_forest_learn(const RandomForestParams &p, const DatasetView &view, 
     };
     {
         unsigned hw = std::thread::hardware_concurrency();
-        // sampling runs on the pool either way; with the device path the tree growth itself is
-        // serialised on the GPU, so a few threads are enough to keep it fed
-        const unsigned nthreads = std::max(1u, std::min<unsigned>(rf.p ? 4u : (hw ? hw : 1u), p.num_trees));
+        const unsigned nthreads =
+            std::max(1u, device_workers ? device_workers : std::min<unsigned>(hw ? hw : 1u, p.num_trees));
         std::vector<std::thread> pool;
-        for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
-        worker();
+        for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker, t);
+        worker(0);
         for (std::thread &t : pool) t.join();
     }
     for (const std::string &f : failures)

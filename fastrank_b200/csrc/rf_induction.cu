@@ -66,19 +66,46 @@ __global__ void __launch_bounds__(kRfThreads) rf_minmax_kernel(RfLevel L) {
     __syncthreads();
     const float *__restrict__ row = L.x + (size_t)L.feats[f] * L.ld;
     const uint32_t i0 = blockIdx.x * kChunk, i1 = min(L.m, i0 + kChunk);
-    for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        const int nid = L.node_of[i];
-        if (nid < 0) continue;
-        const uint32_t p = L.samp_pos[i];
-        const int o = ford(__ldg(row + p));
-        atomicMin(&smn[nid], o);
-        atomicMax(&smx[nid], o);
-        if (labels) {
-            const float g = __ldg(L.gain + p);
-            atomicMin(&sgmn[nid], ford(g));
-            atomicMax(&sgmx[nid], ford(g));
-            atomicAdd(&scnt[nid], 1u);
-            atomicAdd((unsigned long long *)&ssum[nid], (unsigned long long)__double2ll_rn((double)g * kGainScale));
+    // Near the root whole warps sit in one node: such a warp reduces in registers and issues one
+    // shared-memory atomic per quantity instead of 32 colliding ones.
+    for (uint32_t base = i0; base < i1; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const int nid = i < i1 ? L.node_of[i] : -1;
+        int uniform = 0;
+        __match_all_sync(0xffffffffu, nid, &uniform);
+        if (uniform && nid < 0) continue;
+        const uint32_t p = nid >= 0 ? L.samp_pos[i] : 0u;
+        const int o = nid >= 0 ? ford(__ldg(row + p)) : 0;
+        const float g = (labels && nid >= 0) ? __ldg(L.gain + p) : 0.f;
+        const int og = ford(g);
+        const int y = (int)__double2ll_rn((double)g * kGainScale);  // |label| <= 16: fits easily
+        if (uniform) {
+            const int wmn = __reduce_min_sync(0xffffffffu, o), wmx = __reduce_max_sync(0xffffffffu, o);
+            int gmn = 0, gmx = 0, ys = 0;
+            if (labels) {
+                gmn = __reduce_min_sync(0xffffffffu, og);
+                gmx = __reduce_max_sync(0xffffffffu, og);
+                ys = __reduce_add_sync(0xffffffffu, y);
+            }
+            if ((threadIdx.x & 31) == 0) {
+                atomicMin(&smn[nid], wmn);
+                atomicMax(&smx[nid], wmx);
+                if (labels) {
+                    atomicMin(&sgmn[nid], gmn);
+                    atomicMax(&sgmx[nid], gmx);
+                    atomicAdd(&scnt[nid], 32u);
+                    atomicAdd((unsigned long long *)&ssum[nid], (unsigned long long)(long long)ys);
+                }
+            }
+        } else if (nid >= 0) {
+            atomicMin(&smn[nid], o);
+            atomicMax(&smx[nid], o);
+            if (labels) {
+                atomicMin(&sgmn[nid], og);
+                atomicMax(&sgmx[nid], og);
+                atomicAdd(&scnt[nid], 1u);
+                atomicAdd((unsigned long long *)&ssum[nid], (unsigned long long)(long long)y);
+            }
         }
     }
     __syncthreads();
@@ -118,33 +145,66 @@ __global__ void __launch_bounds__(kRfThreads) rf_bucket_kernel(RfLevel L) {
     }
     const float *__restrict__ row = L.x + (size_t)L.feats[f] * L.ld;
     const uint32_t i0 = blockIdx.x * kChunk, i1 = min(L.m, i0 + kChunk);
-    for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        const int nid = L.node_of[i];
-        if (nid < 0) continue;
-        const uint32_t p = L.samp_pos[i];
-        const double v = (double)__ldg(row + p);
-        const double lo = (double)fdro(L.fmin[(size_t)nid * L.F + f]);
-        const double range = __dsub_rn((double)fdro(L.fmax[(size_t)nid * L.F + f]), lo);
+    for (uint32_t base = i0; base < i1; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const int nid = i < i1 ? L.node_of[i] : -1;
+        int uniform = 0;
+        __match_all_sync(0xffffffffu, nid, &uniform);
+        if (uniform && nid < 0) continue;
         uint32_t b = 0;
-        while (b + 1 < k) {
-            const double pos = __dadd_rn(__dmul_rn((double)(b + 1) / (double)k, range), lo);
-            if (v < pos) break;
-            ++b;
+        int y = 0;
+        bool positive = false;
+        if (nid >= 0) {
+            const uint32_t p = L.samp_pos[i];
+            const double v = (double)__ldg(row + p);
+            const double lo = (double)fdro(L.fmin[(size_t)nid * L.F + f]);
+            const double range = __dsub_rn((double)fdro(L.fmax[(size_t)nid * L.F + f]), lo);
+            while (b + 1 < k) {
+                const double pos = __dadd_rn(__dmul_rn((double)(b + 1) / (double)k, range), lo);
+                if (v < pos) break;
+                ++b;
+            }
+            const float g = __ldg(L.gain + p);
+            y = (int)__double2ll_rn((double)g * kGainScale);  // |label| <= 16: |y| <= 2^16
+            positive = g > 0.0f;
         }
-        const float g = __ldg(L.gain + p);
-        const long long y = __double2ll_rn((double)g * kGainScale);
+        if (SMEM && uniform && k <= 8) {
+            // the whole warp sits in one node: per bucket, reduce in registers, one atomic each
+            const long long sq64 = (long long)y * (long long)y;  // up to 2^32: reduced in two 16-bit halves
+            for (uint32_t bb = 0; bb < k; ++bb) {
+                const unsigned in = __ballot_sync(0xffffffffu, b == bb);
+                if (!in) continue;
+                const bool me = b == bb;
+                const int cnt = __popc(in);
+                const int npos = __popc(__ballot_sync(0xffffffffu, me && positive));
+                const int ys = __reduce_add_sync(0xffffffffu, me ? y : 0);
+                const unsigned qlo = __reduce_add_sync(0xffffffffu, me ? (unsigned)(sq64 & 0xffff) : 0u);
+                const unsigned qhi = __reduce_add_sync(0xffffffffu, me ? (unsigned)(sq64 >> 16) : 0u);
+                if ((threadIdx.x & 31) == 0) {
+                    const size_t cell = (size_t)nid * k + bb;
+                    atomicAdd(&sn[cell], (unsigned)cnt);
+                    if (npos) atomicAdd(&spos[cell], (unsigned)npos);
+                    atomicAdd((unsigned long long *)&ssum[cell], (unsigned long long)(long long)ys);
+                    atomicAdd((unsigned long long *)&ssq[cell],
+                              (unsigned long long)(((long long)qhi << 16) + (long long)qlo));
+                }
+            }
+            continue;
+        }
+        if (nid < 0) continue;
+        const long long yl = (long long)y;
         const size_t cell = (size_t)nid * k + b;
         if (SMEM) {
             atomicAdd(&sn[cell], 1u);
-            if (g > 0.0f) atomicAdd(&spos[cell], 1u);
-            atomicAdd((unsigned long long *)&ssum[cell], (unsigned long long)y);
-            atomicAdd((unsigned long long *)&ssq[cell], (unsigned long long)(y * y));
+            if (positive) atomicAdd(&spos[cell], 1u);
+            atomicAdd((unsigned long long *)&ssum[cell], (unsigned long long)yl);
+            atomicAdd((unsigned long long *)&ssq[cell], (unsigned long long)(yl * yl));
         } else {
             const size_t gc = ((size_t)nid * L.F + f) * k + b;
             atomicAdd(&L.b_n[gc], 1u);
-            if (g > 0.0f) atomicAdd(&L.b_pos[gc], 1u);
-            atomicAdd((unsigned long long *)&L.b_sum[gc], (unsigned long long)y);
-            atomicAdd((unsigned long long *)&L.b_sq[gc], (unsigned long long)(y * y));
+            if (positive) atomicAdd(&L.b_pos[gc], 1u);
+            atomicAdd((unsigned long long *)&L.b_sum[gc], (unsigned long long)yl);
+            atomicAdd((unsigned long long *)&L.b_sq[gc], (unsigned long long)(yl * yl));
         }
     }
     if (SMEM) {
