@@ -126,7 +126,8 @@ int fr_dev_device_count(void);
  *   query_index n uint32    dense query number of each instance, in [0, n_queries)
  * Rows are regrouped by query and, inside a query, ordered by (gain asc, instance id asc) --
  * the reference's tie-break (evaluators.rs:33-49) -- so that ranking on the device is a
- * stable descending sort by score. */
+ * stable descending sort by score.  Queries may have any length: lists of up to 1024 documents
+ * are ranked in shared memory, longer ones from HBM. */
 int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const float *gains,
                           const uint32_t *query_index, uint32_t n_queries, fr_dev_dataset **out);
 void fr_dev_dataset_destroy(fr_dev_dataset *ds);
