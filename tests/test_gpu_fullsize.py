@@ -101,3 +101,57 @@ def test_full_size_row_permutation_invariance(full):
             d2.close()
     # random float features: no score ties inside a query, so the id tie-break cannot matter
     assert out[0] == out[1]
+
+
+@pytest.mark.parametrize("name,metric,depth", [("map", 1, -1), ("rr", 2, -1), ("ndcg", 0, -1), ("ndcg@3", 0, 3)])
+def test_full_size_other_metrics_fast_vs_exact(oracle, full, name, metric, depth):
+    X, y, qid, dev, nq = full
+    rng = np.random.default_rng(13)
+    base = rng.uniform(-1, 1, size=(3, D))
+    base /= np.abs(base).sum(axis=1, keepdims=True)
+    fids = [5, 77, 135]
+    cands = [[0.0, base[r, fids[r]] - 0.05, base[r, fids[r]] + 0.4, 3.0] for r in range(3)]
+    plan = dev.plan(metric, depth)
+    fast = plan.coord_sweeps(base, fids, cands, fast=True)
+    exact = plan.coord_sweeps(base, fids, cands)
+    assert (np.abs(fast - exact).astype(np.float64) / FX / nq).max() < 1e-9
+    # and the exact kernel against the oracle on a query sample, per query
+    uq = np.unique(qid)
+    pick = np.sort(rng.choice(len(uq), 200, replace=False))
+    rows = np.nonzero(np.isin(qid, uq[pick]))[0]
+    Xs, ys, qs = np.ascontiguousarray(X[rows]), y[rows], qid[rows]
+    ods = oracle_dataset(oracle, Xs, ys, qs)
+    w = base[1].copy()
+    w[fids[1]] = cands[1][2]
+    _, pq = plan.eval_linear(w[None, :])
+    exp = oracle.evaluate_scores(ods, oracle.score_linear(Xs, w), name)
+    assert np.array_equal(pq[0][pick], exp)
+
+
+def test_full_size_forest_scoring(oracle):
+    """BASELINE configs[3] at full size: a depth-8 forest over 1M x 136.  Scores bit-identical to
+    the oracle on a row sample; linearity of the ensemble sum (score([A, B]) == score(A) +
+    score(B) exactly, weights 1.0) and idempotence over all rows."""
+    import fastrank_b200 as fr
+
+    X, y, qid = synth(N, D, Q)
+    rng = np.random.default_rng(14)
+
+    def tree(depth):
+        if depth >= 8 or (depth > 2 and rng.random() < 0.05):
+            return {"LeafNode": float(np.round(rng.uniform(0, 4), 3))}
+        fid = int(rng.integers(0, D))
+        split = float(np.quantile(X[:2000, fid], rng.uniform(0.1, 0.9)))
+        return {"FeatureSplit": {"fid": fid, "split": split, "lhs": tree(depth + 1), "rhs": tree(depth + 1)}}
+
+    a = [{"DecisionTree": tree(1)} for _ in range(30)]
+    b = [{"DecisionTree": tree(1)} for _ in range(30)]
+    ens = lambda ms: {"Ensemble": {"weights": [1.0] * len(ms), "models": ms}}  # noqa: E731
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    sa = fr.CModel.from_dict(ens(a)).predict_dense(ds)
+    sb = fr.CModel.from_dict(ens(b)).predict_dense(ds)
+    sab = fr.CModel.from_dict(ens([ens(a), ens(b)])).predict_dense(ds)
+    assert np.array_equal(sab, sa + sb)
+    assert np.array_equal(fr.CModel.from_dict(ens(a)).predict_dense(ds), sa)
+    rows = np.sort(rng.choice(N, 20000, replace=False))
+    assert np.array_equal(sa[rows], oracle.score_model(np.ascontiguousarray(X[rows]), ens(a)))
