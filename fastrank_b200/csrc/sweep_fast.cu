@@ -60,6 +60,7 @@ struct FastArgs {
     unsigned char *const *mail_peers;  // [world] every rank's mailbox, own included
     unsigned *done_ctr;                // CTAs that have flushed their sums (zeroed before the launch)
     uint32_t mail_rank, mail_world, mail_epoch, mail_words;
+    uint32_t n_split;  // tiles handed out as quarter items (the last ones of the queue)
 };
 
 // system-scope flag accesses for the peer mailboxes
@@ -243,7 +244,7 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     // Work items: whole tiles first; the last n_split tiles are handed out as quarter items (a
     // quarter of the row groups each, phase 1 repeated) so that the final wave of the persistent
     // grid is made of short items and the SMs drain together.
-    const uint32_t n_split = G >= 4 ? min(P.nt, gridDim.x / 4u) : 0u;
+    const uint32_t n_split = G >= 4 ? min(P.nt, A.n_split) : 0u;
     const uint32_t n_whole = P.nt - n_split;
     const uint32_t n_items = G > 0 ? n_whole + 4u * n_split : 0u;
     uint32_t next_item = n_items;
@@ -536,6 +537,10 @@ int launch_fast(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStrea
     uint32_t gx = (uint32_t)std::max<uint64_t>(1, total / n_groups);
     if (gx > pl->nt) gx = std::max<uint32_t>(pl->nt, 1);  // an empty shard still takes part in the reduction
     PlanView pv = pl->view();
+    FastArgs args = a;
+    // quarter items: the last gx / 4 tiles, one final wave of short items (splitting every tile
+    // of a small shard was measured and is slower: phase 1 is repeated per item)
+    args.n_split = gx / 4u;
     FastView fv;
     fv.tile_task_off = pl->fast.tile_task_off.p;
     fv.tasks = pl->fast.tasks.p;
@@ -545,7 +550,7 @@ int launch_fast(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStrea
     fv.n_cls = pl->fast.n_cls;
     auto *ev = pl->ds->prof_slot();
     if (ev) cudaEventRecord(ev->first, stream);
-    kernel<<<dim3(gx, n_groups), TB, L.total, stream>>>(pv, fv, a);
+    kernel<<<dim3(gx, n_groups), TB, L.total, stream>>>(pv, fv, args);
     if (ev) cudaEventRecord(ev->second, stream);
     LAUNCHED();
     CU(cudaGetLastError());
