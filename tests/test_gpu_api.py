@@ -529,3 +529,44 @@ def test_device_forest_is_deterministic_and_agrees_with_the_host_trainer(fr, mon
     assert out["gpu"][0][1] == pytest.approx(out["host"][0][1], abs=2e-3)
     same = sum(a == b for a, b in zip(out["gpu"][0][0]["Ensemble"]["models"], out["host"][0][0]["Ensemble"]["models"]))
     assert same >= 4  # identical trees unless a near-tie was broken the other way
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_coordinate_ascent_trajectories_match_the_oracle_driver(fr, oracle, case):
+    """Randomised configurations of the whole learner: the GPU-backed state machine (all restarts
+    and all three directions per launch, speculative results discarded on an early break) must
+    walk exactly the path of the sequential restatement of coordinate_ascent.rs -- same number of
+    consumed evaluations, same final weights -- for every measure, with and without normalisation
+    and random initialisation, including degenerate shapes (one feature, one query, no relevant
+    document anywhere)."""
+    rng = np.random.default_rng(500 + case)
+    n = int(rng.integers(40, 1500))
+    d = int(rng.integers(1, 7))
+    q = int(rng.integers(1, max(2, n // 8)))
+    qid = np.sort(rng.integers(0, q, n)).astype(np.int64)
+    if case % 2 == 0:
+        X = rng.integers(-3, 4, size=(n, d)).astype(np.float32)       # exact arithmetic, many ties
+    else:
+        X = rng.normal(size=(n, d)).astype(np.float32)
+    y = rng.integers(0, 4, n).astype(np.float64) * (rng.random(n) < 0.6)
+    if case == 5:
+        y[:] = 0.0                                                    # nothing relevant: every mean is 0
+    measure = ["ndcg@10", "map", "rr", "ndcg", "ndcg@3", "map", "ndcg@1", "rr"][case]
+    kw = dict(num_restarts=int(rng.integers(1, 5)), num_max_iterations=int(rng.integers(1, 9)),
+              step_base=float(rng.choice([0.05, 0.5, 1.0])), step_scale=float(rng.choice([2.0, 1.5])),
+              tolerance=float(rng.choice([0.001, 0.0, 0.01])), seed=int(rng.integers(0, 2 ** 40)),
+              normalize=bool(case % 3), init_random=bool(case % 4))
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    ods = oracle_dataset(oracle, X, y, qid)
+    req = fr.TrainRequest.coordinate_ascent()
+    req.measure = measure
+    req.params.quiet = True
+    for k, v in kw.items():
+        setattr(req.params, k, v)
+    m = ds.train_model(req)
+    res = oracle.coordinate_ascent(ods, measure, **kw)
+    stats = fr.query_json("last_train_stats")
+    assert stats["evals_consumed"] == res["n_evals"], (case, kw)
+    w = np.asarray(m.to_dict()["Linear"]["weights"])
+    assert np.allclose(w, res["weights"], rtol=0, atol=1e-12), (case, kw)
+    assert ds.evaluate_mean(m, measure) == pytest.approx(res["score"], abs=1e-12)
