@@ -101,11 +101,10 @@ struct SlotType<256> {
 };
 
 struct SmemLayout {
-    size_t score, roww, sum, tbl, gexp, slot0, slot1, tasks, cls, rowsw, misc, w, total;
+    size_t score, sum, tbl, gexp, slot0, slot1, tasks, cls, rowsw, misc, w, total;
     __host__ __device__ SmemLayout(int tb, int slot_bytes, uint32_t w_doubles) {
         size_t o = 0;
         score = o;  o += align16(sizeof(double) * 32 * (size_t)(tb + 1));
-        roww = o;
         sum = o;    o += sizeof(unsigned long long) * kMaxRows;
         tbl = o;    // the discount table and the per-document gains are never live together
         gexp = o;   o += sizeof(double) * (tb > kSmemTbl ? tb : kSmemTbl);

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kTile) forest_tile_kernel(const float *__restr
                                                             const uint32_t *__restrict__ inst_of_pos,
                                                             double *__restrict__ out_pos,
                                                             double *__restrict__ out_inst) {
-    extern __shared__ __align__(16) float xs[];  // [dstage][kTile]
+    extern __shared__ __align__(128) float xs[];  // [dstage][kTile]
     const int t = threadIdx.x;
     const size_t p0 = (size_t)blockIdx.x * kTile;
     // stage: thread t copies 4 consecutive positions of feature row f = it * 4 + t / 32
