@@ -20,7 +20,12 @@
 //            (FP64 pipe) + one predicated add (integer pipe) per comparison.
 //            rank -> slot[rank] = gain class; one warp per query then folds the slots in rank
 //            order (the reference's left-to-right f64 sums over a host-built table of
-//            (2^gain - 1) / log2(rank + 2)) and accumulates round(value * 2^40).
+//            (2^gain - 1) / log2(rank + 2)) and accumulates round(value * 2^40).  The folds of
+//            group g ride in the task queue of group g + 1.
+//   tail     multi-GPU: the last CTA to finish exchanges the GPU's integer sums with every peer
+//            through NVLink-mapped mailboxes and leaves the total in place (no collective launch).
+// Scheduling: work items come from an atomic counter -- whole tiles first, the last gridDim.x / 4
+// tiles as quarter items (a quarter of the row groups each) so that the SMs drain together.
 //
 // Arithmetic contract ("fast" mode): a candidate's score is the reference's dot product with
 // the varied coordinate's term added last instead of in position -- a few roundings apart
