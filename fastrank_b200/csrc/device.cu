@@ -20,6 +20,7 @@
 // Determinism: per-query metric values are bit-identical to the oracle; they are summed as
 // signed fixed point (2^-40) with integer atomics, so the mean does not depend on launch
 // geometry, atomics order or the number of GPUs.
+#include <chrono>
 #include <thread>
 
 #include "device_common.cuh"
@@ -597,11 +598,19 @@ int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const 
     ds->ld = (n + 127) / 128 * 128;
     ds->nq = n_queries;
     CU(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
+    const bool trace = getenv("FASTRANK_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (trace)
+            fprintf(stderr, "[fastrank_b200] dataset_create %-14s +%.1f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     // The row-major matrix goes up on a helper thread (a pageable copy blocks its caller for the
     // whole transfer) while this thread builds the query / gain ordering the transpose needs.
     DevBuf<float> staging;
     CU(staging.alloc(n * d));
     CU(ds->x.alloc(ds->ld * d));
+    lap("alloc");
     cudaError_t copy_status = cudaSuccess;
     std::thread copier([&]() {
         copy_status = cudaSetDevice(device);
@@ -636,15 +645,31 @@ int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const 
         for (size_t i = 0; i < n; ++i) ds->inst_of_pos[fill[query_index[i]]++] = (uint32_t)i;
     }
     for (uint32_t q = 0; q < n_queries; ++q) {
-        auto b = ds->inst_of_pos.begin() + ds->q_start[q];
-        std::stable_sort(b, b + ds->q_len[q],
-                         [&](uint32_t a, uint32_t c) { return gains[a] < gains[c]; });
+        uint32_t *b = ds->inst_of_pos.data() + ds->q_start[q];
+        const uint32_t len = ds->q_len[q];
+        if (len <= 64) {  // typical lists: a stable insertion sort, no allocation
+            for (uint32_t i = 1; i < len; ++i) {
+                const uint32_t v = b[i];
+                const float g = gains[v];
+                uint32_t j = i;
+                while (j > 0 && gains[b[j - 1]] > g) {
+                    b[j] = b[j - 1];
+                    --j;
+                }
+                b[j] = v;
+            }
+        } else {
+            std::stable_sort(b, b + len, [&](uint32_t a, uint32_t c) { return gains[a] < gains[c]; });
+        }
     }
     ds->pos_of_inst.resize(n);
     ds->gain_pos.resize(n);
     std::vector<double> gexp(n);
     {
-        std::map<uint32_t, double> cache;  // 2^gain - 1 with the host libm, as the oracle does
+        // 2^gain - 1 with the host libm, as the oracle does; labels take a handful of distinct
+        // values, so a flat cache probed from the most recent entry beats a tree
+        std::vector<std::pair<uint32_t, double>> cache;
+        size_t last = 0;
         for (size_t p = 0; p < n; ++p) {
             const uint32_t inst = ds->inst_of_pos[p];
             ds->pos_of_inst[inst] = (uint32_t)p;
@@ -652,17 +677,23 @@ int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const 
             ds->gain_pos[p] = g;
             uint32_t bits;
             memcpy(&bits, &g, 4);
-            auto it = cache.find(bits);
-            if (it == cache.end()) it = cache.emplace(bits, std::pow(2.0, (double)g) - 1.0).first;
-            gexp[p] = it->second;
+            if (cache.empty() || cache[last].first != bits) {
+                size_t at = 0;
+                while (at < cache.size() && cache[at].first != bits) ++at;
+                if (at == cache.size()) cache.emplace_back(bits, std::pow(2.0, (double)g) - 1.0);
+                last = at;
+            }
+            gexp[p] = cache[last].second;
         }
     }
     cudaStream_t s = ds->stream;
     CU(ds->gain.upload(ds->gain_pos, s));
     CU(ds->gexp.upload(gexp, s));
     CU(ds->inst_of_pos_dev.upload(ds->inst_of_pos, s));
+    lap("host index");
     copier.join();
     CU(copy_status);
+    lap("matrix copied");
     {
         dim3 grid((unsigned)((ds->ld + 31) / 32), (unsigned)((d + 31) / 32));
         gather_transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(staging.p, ds->inst_of_pos_dev.p,
@@ -671,6 +702,8 @@ int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const 
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(s));
     }
+    staging.release();
+    lap("transposed");
     *out = ds.release();
     return 0;
 }

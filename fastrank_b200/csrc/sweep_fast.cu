@@ -581,25 +581,30 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
     fp.td = td;
     const bool ndcg = pl->metric == FR_METRIC_NDCG;
     // gain classes
-    std::map<uint32_t, uint32_t> cls_of_bits;
+    std::vector<uint32_t> cls_bits;  // bit pattern of class c's gain (flat: a handful of classes)
     std::vector<float> cls_gain;
     std::vector<uint8_t> pd_cls(pd_pos.size(), 0);
     bool table = ndcg;
     if (table) {
+        size_t last = 0;
         for (size_t i = 0; i < pd_pos.size(); ++i) {
             const float g = ds->gain_pos[pd_pos[i]];
             uint32_t bits;
             memcpy(&bits, &g, 4);
-            auto it = cls_of_bits.find(bits);
-            if (it == cls_of_bits.end()) {
-                if (cls_gain.size() >= 255) {
-                    table = false;
-                    break;
+            if (cls_bits.empty() || cls_bits[last] != bits) {
+                size_t at = 0;
+                while (at < cls_bits.size() && cls_bits[at] != bits) ++at;
+                if (at == cls_bits.size()) {
+                    if (cls_gain.size() >= 255) {
+                        table = false;
+                        break;
+                    }
+                    cls_bits.push_back(bits);
+                    cls_gain.push_back(g);
                 }
-                it = cls_of_bits.emplace(bits, (uint32_t)cls_gain.size()).first;
-                cls_gain.push_back(g);
+                last = at;
             }
-            pd_cls[i] = (uint8_t)it->second;
+            pd_cls[i] = (uint8_t)last;
         }
     }
     cudaStream_t s = ds->stream;
