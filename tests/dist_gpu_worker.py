@@ -23,6 +23,16 @@ def workload():
     return X, y, qid, base, fids, cands, W
 
 
+def many_rows():
+    """8 sweeps x 80 candidates: more rows than one pass holds, so the cross-GPU reduction has to
+    ride on the LAST pass only."""
+    rng = np.random.default_rng(2)
+    base = rng.normal(size=(8, 24))
+    fids = [int(v) for v in rng.integers(0, 24, 8)]
+    cands = [[float(v) for v in rng.normal(size=80)] for _ in range(8)]
+    return base, fids, cands
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -48,6 +58,8 @@ def main():
     fast = plan.coord_sweeps(base, fids, cands, fast=True)
     exact = plan.coord_sweeps(base, fids, cands)
     lin, _ = plan.eval_linear(W, per_query=False)
+    mbase, mfids, mcands = many_rows()
+    many = plan.coord_sweeps(mbase, mfids, mcands, fast=True)
     nq_global = int(lib.fr_dev_plan_global_queries(plan.ptr))
     dev.close()
     # the reference-compatible surface on a shard: train_model sees all-reduced means
@@ -61,7 +73,8 @@ def main():
     weights = model.to_dict()["Linear"]["weights"]
     mean = ds.evaluate_mean(model, "ndcg@10")
     gathered = [None] * world
-    dist.all_gather_object(gathered, (fast.tolist(), exact.tolist(), lin.tolist(), nq_global, weights, mean))
+    dist.all_gather_object(gathered, (fast.tolist(), exact.tolist(), lin.tolist(), nq_global, weights, mean,
+                                      many.tolist()))
     if rank == 0:
         with open(out_path, "w") as fp:
             json.dump({"world": world, "ranks": gathered}, fp)

@@ -26,7 +26,7 @@ def test_two_ranks_match_one_gpu(tmp_path):
     import fastrank_b200 as fr
     from fastrank_b200._native import lib
     from fastrank_b200.kernels import DevDataset, dense_query_index
-    from tests.dist_gpu_worker import workload
+    from tests.dist_gpu_worker import many_rows, workload
 
     if lib.fr_dev_device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -46,6 +46,8 @@ def test_two_ranks_match_one_gpu(tmp_path):
         fast = plan.coord_sweeps(base, fids, cands, fast=True)
         exact = plan.coord_sweeps(base, fids, cands)
         lin, _ = plan.eval_linear(W, per_query=False)
+        mbase, mfids, mcands = many_rows()
+        many = plan.coord_sweeps(mbase, mfids, mcands, fast=True)
     finally:
         dev.close()
     ds = fr.CDataset.from_numpy(X, y, qid)
@@ -55,7 +57,8 @@ def test_two_ranks_match_one_gpu(tmp_path):
     req.params.seed = 7
     req.params.quiet = True
     model = ds.train_model(req)
-    for r_fast, r_exact, r_lin, nq_global, weights, mean in got["ranks"]:
+    for r_fast, r_exact, r_lin, nq_global, weights, mean, r_many in got["ranks"]:
+        assert r_many == many.tolist()
         assert nq_global == nq
         assert r_exact == exact.tolist()   # fixed-point sums do not depend on the sharding
         assert r_fast == fast.tolist()

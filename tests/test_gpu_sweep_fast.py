@@ -235,3 +235,26 @@ def test_fast_sweep_reports_nan(oracle):
             plan.coord_sweeps(np.array([[np.nan, 0.0, 0.0, 0.0]]), [1], [[0.0, 1.0]], fast=True)
     finally:
         dev.close()
+
+
+def test_more_rows_than_one_pass_holds(oracle):
+    """8 sweeps x 80 candidates = 640 rows: a sweep group takes 512 rows per pass over X, so the
+    call needs a second pass; 3 sweeps x 200 candidates exercises an uneven split."""
+    X, y, qid, ods, dev = _mk(oracle, 3000, 10, 90, seed=17)
+    rng = np.random.default_rng(6)
+    try:
+        plan = dev.plan(0, 10)
+        for n_sweeps, ncand in ((8, 80), (3, 200)):
+            base = rng.normal(size=(n_sweeps, 10))
+            fids = [int(v) for v in rng.integers(0, 10, n_sweeps)]
+            cands = [[float(v) for v in rng.normal(size=ncand)] for _ in range(n_sweeps)]
+            fast = plan.coord_sweeps(base, fids, cands, fast=True)
+            exact = plan.coord_sweeps(base, fids, cands)
+            assert np.abs(fast - exact).max() / FX / 90 < 1e-9
+            for r, k in ((0, 0), (n_sweeps - 1, ncand - 1), (1, ncand // 2)):
+                w = base[r].copy()
+                w[fids[r]] = cands[r][k]
+                exp = oracle.evaluate_scores(ods, oracle.score_linear(X, w), "ndcg@10")
+                assert abs(int(fast[r, k]) - fx_sum(exp)) / FX / 90 < 1e-9
+    finally:
+        dev.close()
