@@ -50,70 +50,133 @@ __global__ void gather_transpose_kernel(const float *__restrict__ src,
     }
 }
 
-// Order-preserving map f64 -> u64 (larger score => larger key).  NotNan ordering treats
-// -0.0 and +0.0 as equal (evaluators.rs:36), so zeros are canonicalised first.
-__device__ __forceinline__ unsigned long long score_key(double s, int *err_flag) {
-    if (s != s) atomicOr(err_flag, ERR_NAN_SCORE);  // reference: panic "Model.predict -> NaN"
-    long long b = __double_as_longlong(s);
-    if ((b << 1) == 0) b = 0;
-    unsigned long long u = (unsigned long long)b;
-    return b < 0 ? ~u : (u | 0x8000000000000000ull);
+// ---- shared-memory layout of the ranking kernels -------------------------------------------
+//   s_sc    f64 [TB][SROW]  scores, one row per local document (row stride chosen so that the
+//                           128-bit row reads of a quarter warp fall into distinct banks)
+//   s_slot  u64 [TB][KC]    metric payload by (query start + rank)
+//   s_ge    f64 [TB]        2^gain - 1 of the local document (NDCG)
+//   s_sum   u64 [KC]        fixed-point metric sums of this CTA
+//   s_q     u32 [TB]        packed (query start | query end << 16) of the local document
+//   s_wcnt  u32 [32]        contributing documents per warp
+//   s_list  u16 [TB]        local documents whose rank matters, compacted
+__host__ __device__ constexpr int eval_srow(int kc) {
+    return kc == 1 ? 1 : (kc % 4 == 2 ? kc : kc + 2);
+}
+__host__ __device__ constexpr size_t eval_words(int kc, int tb) {  // 8-byte words before s_q
+    return (size_t)eval_srow(kc) * tb + (size_t)kc * tb + tb + kc;
+}
+template <int KC>
+__device__ __forceinline__ unsigned long long *eval_sum_ptr(unsigned long long *smem, int tb) {
+    return smem + (size_t)eval_srow(KC) * tb + (size_t)KC * tb + tb;
+}
+
+// cnt += (sj > my) || (sj == my && before): the document at j outranks mine
+// (evaluators.rs:33-49: score descending; on equal scores the earlier local position wins,
+// local order being the reference's gain-ascending / id-ascending tie-break).  DSETP compares
+// -0.0 == +0.0 like NotNan does (evaluators.rs:36); NaN scores are reported before ranking.
+__device__ __forceinline__ void count_outranks(unsigned &cnt, double sj, double my, unsigned before) {
+    asm("{ .reg .pred p, q; setp.ne.u32 q, %3, 0; setp.eq.and.f64 p, %1, %2, q;"
+        " setp.gt.or.f64 p, %1, %2, p; @p add.u32 %0, %0, 1; }"
+        : "+r"(cnt)
+        : "d"(sj), "d"(my), "r"(before));
 }
 
 // Rank one tile for up to KC candidates and fold the per-query metric into s_sum.
 //
-// keys[k][t] holds the key of local document t under candidate k.  Because local order is the
-// reference's tie-break order, rank(t) = #{j : key_j > key_t} + #{j < t : key_j == key_t}
-// (evaluators.rs:33-49).  Each document then drops its metric payload into slot rank(t) of its
-// query, and one thread per (query, candidate) folds the slots in rank order -- the same
-// left-to-right f64 sums the reference performs (evaluators.rs:265-270, :434-446).
+// sc[k] is the score of this thread's local document under candidate k.  Only documents whose
+// rank matters are ranked (2^gain - 1 != 0 for NDCG, gain > 0 for AP / RR: every other document
+// adds +0.0 or nothing, evaluators.rs:91-93, :265-270): they are compacted so that whole warps
+// count, rank(t) = #{j : s_j > s_t} + #{j < t : s_j == s_t}.  Each ranked document drops its
+// metric payload into slot rank(t) of its query, and one thread per (query, candidate) folds the
+// slots in rank order -- the same left-to-right f64 sums the reference performs
+// (evaluators.rs:265-270, :434-446).
 template <int KC>
 __device__ __forceinline__ void rank_and_metric(const PlanView &P, uint32_t tile, int tb, int t,
-                                                bool active, uint32_t qs, uint32_t qe, uint32_t pos,
-                                                const unsigned long long (&mykey)[KC], int K,
-                                                unsigned long long *s_keys,
-                                                unsigned long long *s_sum, double *g_perq,
+                                                bool active, uint32_t qp, uint32_t pos,
+                                                const double (&sc)[KC], int K,
+                                                unsigned long long *smem, double *g_perq,
                                                 int *g_err) {
+    static_assert(KC == 1 || KC % 2 == 0, "candidates are read in pairs");
+    constexpr int SROW = eval_srow(KC);
+    double *s_sc = reinterpret_cast<double *>(smem);
+    unsigned long long *s_slot = smem + (size_t)SROW * tb;
+    double *s_ge = reinterpret_cast<double *>(s_slot + (size_t)KC * tb);
+    unsigned long long *s_sum = reinterpret_cast<unsigned long long *>(s_ge + tb);
+    uint32_t *s_q = reinterpret_cast<uint32_t *>(smem + eval_words(KC, tb));
+    uint32_t *s_wcnt = s_q + tb;
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_wcnt + 32);
+    const int lane = t & 31, warp = t >> 5;
+
+    bool contrib = false;
     if (active) {
+        bool nan = false;
 #pragma unroll
-        for (int k = 0; k < KC; ++k)
-            if (k < K) s_keys[k * tb + t] = mykey[k];
+        for (int k = 0; k < KC; ++k) {
+            nan |= k < K && sc[k] != sc[k];
+            s_sc[(size_t)t * SROW + k] = sc[k];
+            s_slot[(size_t)t * KC + k] = 0ull;
+        }
+        if (nan) atomicOr(g_err, ERR_NAN_SCORE);  // reference: panic "Model.predict -> NaN"
+        s_q[t] = qp;
+        if (P.metric == FR_METRIC_NDCG) {
+            const double ge = __ldg(P.gexp + pos);
+            s_ge[t] = ge;
+            contrib = ge != 0.0;
+        } else {
+            contrib = __ldg(P.gain + pos) > 0.0f;  // evaluators.rs:91-93
+        }
     }
+    const unsigned ballot = __ballot_sync(0xffffffffu, contrib);
+    if (lane == 0) s_wcnt[warp] = (uint32_t)__popc(ballot);
     __syncthreads();
-    unsigned cnt[KC];
+    unsigned before_me = 0, total = 0;
+    for (int w = 0; w < (tb >> 5); ++w) {
+        const unsigned c = s_wcnt[w];
+        before_me += w < warp ? c : 0u;
+        total += c;
+    }
+    if (contrib) s_list[before_me + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)t;
+    __syncthreads();
+
+    if ((unsigned)t < total) {
+        const int d = s_list[t];
+        const uint32_t qq = s_q[d];
+        const int qs = (int)(qq & 0xffffu), qe = (int)(qq >> 16);
+        double my[KC];
+        unsigned cnt[KC];
 #pragma unroll
-    for (int k = 0; k < KC; ++k) cnt[k] = 0;
-    if (active) {
-        for (uint32_t j = qs; j < qe; ++j) {
-            const bool before = j < (uint32_t)t;
+        for (int k = 0; k < KC; ++k) {
+            my[k] = s_sc[(size_t)d * SROW + k];
+            cnt[k] = 0;
+        }
+#pragma unroll 2
+        for (int j = qs; j < qe; ++j) {
+            const unsigned before = j < d ? 1u : 0u;
+            const double *row = s_sc + (size_t)j * SROW;
+            if (KC == 1) {
+                count_outranks(cnt[0], row[0], my[0], before);
+            } else {
 #pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                if (k < K) {
-                    unsigned long long kj = s_keys[k * tb + j];
-                    cnt[k] += (kj > mykey[k]) | ((kj == mykey[k]) & before);
+                for (int k = 0; k < KC; k += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(row + k);
+                    count_outranks(cnt[k], v.x, my[k], before);
+                    count_outranks(cnt[k + 1], v.y, my[k + 1], before);
                 }
             }
         }
-    }
-    __syncthreads();
-    if (active) {
-        const float g = __ldg(P.gain + pos);
         if (P.metric == FR_METRIC_NDCG) {
-            const double ge = __ldg(P.gexp + pos);
+            const double ge = s_ge[d];
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
-                if (k < K) {
-                    double term = 0.0;
-                    // compute_dcg, evaluators.rs:265-270: (2^gain - 1) / log2(i + 2)
-                    if ((int)cnt[k] < P.depth && ge != 0.0) term = ge / __ldg(P.lg2 + cnt[k]);
-                    s_keys[k * tb + qs + cnt[k]] = (unsigned long long)__double_as_longlong(term);
-                }
+                // compute_dcg, evaluators.rs:265-270: (2^gain - 1) / log2(i + 2)
+                if (k < K && (int)cnt[k] < P.depth)
+                    s_slot[(size_t)(qs + cnt[k]) * KC + k] =
+                        (unsigned long long)__double_as_longlong(ge / __ldg(P.lg2 + cnt[k]));
             }
         } else {
-            const unsigned long long rel = g > 0.0f ? 1ull : 0ull;  // evaluators.rs:91-93
 #pragma unroll
             for (int k = 0; k < KC; ++k)
-                if (k < K) s_keys[k * tb + qs + cnt[k]] = rel;
+                if (k < K) s_slot[(size_t)(qs + cnt[k]) * KC + k] = 1ull;
         }
     }
     __syncthreads();
@@ -124,7 +187,7 @@ __device__ __forceinline__ void rank_and_metric(const PlanView &P, uint32_t tile
         const uint32_t pq = q0 + ql;
         const uint32_t loc = P.pq_local[pq];
         const uint32_t start = loc & 0xffffu, len = loc >> 16;
-        const unsigned long long *slots = s_keys + k * tb + start;
+        const unsigned long long *slots = s_slot + (size_t)start * KC + k;
         const double norm = P.pq_norm[pq];
         double value = 0.0;
         if (P.metric == FR_METRIC_NDCG) {
@@ -132,7 +195,7 @@ __device__ __forceinline__ void rank_and_metric(const PlanView &P, uint32_t tile
                 const uint32_t lim = len < (uint32_t)P.depth ? len : (uint32_t)P.depth;
                 double dcg = 0.0;
                 for (uint32_t r = 0; r < lim; ++r)
-                    dcg = __dadd_rn(dcg, __longlong_as_double((long long)slots[r]));
+                    dcg = __dadd_rn(dcg, __longlong_as_double((long long)slots[(size_t)r * KC]));
                 if (dcg > norm) atomicOr(g_err, ERR_DCG_ABOVE_IDEAL);  // evaluators.rs:369-374
                 value = dcg / norm;
             }
@@ -141,7 +204,7 @@ __device__ __forceinline__ void rank_and_metric(const PlanView &P, uint32_t tile
                 unsigned recall = 0;
                 double sum = 0.0;
                 for (uint32_t r = 0; r < len; ++r) {
-                    if (slots[r]) {
+                    if (slots[(size_t)r * KC]) {
                         recall += 1;
                         sum = __dadd_rn(sum, (double)recall / (double)(r + 1));
                     }
@@ -150,7 +213,7 @@ __device__ __forceinline__ void rank_and_metric(const PlanView &P, uint32_t tile
             }
         } else {
             for (uint32_t r = 0; r < len; ++r) {
-                if (slots[r]) {
+                if (slots[(size_t)r * KC]) {
                     value = 1.0 / (double)(r + 1);
                     break;
                 }
@@ -182,9 +245,8 @@ struct SweepArgs {
 // bit-identical to dense_dataset.rs:67-76.
 template <int KC, int TB>
 __global__ void __launch_bounds__(TB) coord_sweep_kernel(PlanView P, SweepArgs A) {
-    extern __shared__ unsigned long long smem[];
-    unsigned long long *s_keys = smem;             // KC * TB
-    unsigned long long *s_sum = smem + KC * TB;    // KC
+    extern __shared__ __align__(16) unsigned long long smem[];
+    unsigned long long *s_sum = eval_sum_ptr<KC>(smem, TB);
     const int t = threadIdx.x;
     const uint32_t sweep = blockIdx.y;
     const int ncand = (int)A.n_cand[sweep] - (int)A.cand_off;
@@ -200,20 +262,19 @@ __global__ void __launch_bounds__(TB) coord_sweep_kernel(PlanView P, SweepArgs A
         const uint32_t doc0 = P.tile_doc_off[tile];
         const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
         const bool active = t < nd;
-        uint32_t pos = 0, qs = 0, qe = 0;
-        unsigned long long key[KC];
+        uint32_t pos = 0, qp = 0;
+        double tk[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) tk[k] = 0.0;
         if (active) {
             pos = P.pd_pos[doc0 + t];
-            const uint32_t qp = P.pd_q[doc0 + t];
-            qs = qp & 0xffffu;
-            qe = qp >> 16;
+            qp = P.pd_q[doc0 + t];
             const float *__restrict__ xp = P.x + pos;
             double acc = 0.0;
             const uint32_t fsplit = f < dm ? f : dm;
 #pragma unroll 8
             for (uint32_t j = 0; j < fsplit; ++j)
                 acc = __dadd_rn(acc, __dmul_rn((double)__ldg(xp + (size_t)j * P.ld), __ldg(w + j)));
-            double tk[KC];
             if (f < dm) {
                 const double xf = (double)__ldg(xp + (size_t)f * P.ld);
 #pragma unroll
@@ -231,14 +292,8 @@ __global__ void __launch_bounds__(TB) coord_sweep_kernel(PlanView P, SweepArgs A
 #pragma unroll
                 for (int k = 0; k < KC; ++k) tk[k] = acc;
             }
-#pragma unroll
-            for (int k = 0; k < KC; ++k) key[k] = k < K ? score_key(tk[k], A.err) : 0ull;
-        } else {
-#pragma unroll
-            for (int k = 0; k < KC; ++k) key[k] = 0ull;
         }
-        rank_and_metric<KC>(P, tile, TB, t, active, qs, qe, pos, key, K, s_keys, s_sum, nullptr,
-                            A.err);
+        rank_and_metric<KC>(P, tile, TB, t, active, qp, pos, tk, K, smem, nullptr, A.err);
     }
     if (t < K)
         atomicAdd((unsigned long long *)(A.sums + (size_t)sweep * A.cand_stride + A.cand_off + t),
@@ -250,50 +305,112 @@ struct BatchArgs {
     long long *sums;    // [KC]
     double *perq;       // nullptr or [KC][nq_view]
     uint32_t dm;
+    uint32_t wchunk;    // features whose weights fit the shared-memory staging area at once
     int K;
     int *err;
 };
 
+// X is read once per launch: keep it out of L1 (the per-document plan arrays stay there).
+__device__ __forceinline__ float ld_x(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+__host__ __device__ constexpr size_t eval_smem_bytes_c(int kc, int tb) {
+    return ((8 * eval_words(kc, tb) + 4 * (size_t)tb + 4 * 32 + 2 * (size_t)tb) + 15) / 16 * 16;
+}
+
 // evaluate_mean for KC arbitrary weight vectors in one pass over X (evaluators.rs:173-224).
+// One thread scores one document for all KC candidates: x_j is read once (coalesced along the
+// document axis of the feature-major matrix), the KC weights of feature j come from shared
+// memory as 128-bit broadcasts, and every candidate keeps the reference's left-to-right f64 sum
+// with separate multiply and add (dense_dataset.rs:67-76).
 template <int KC, int TB>
 __global__ void __launch_bounds__(TB) linear_batch_kernel(PlanView P, BatchArgs A) {
-    extern __shared__ unsigned long long smem[];
-    unsigned long long *s_keys = smem;
-    unsigned long long *s_sum = smem + KC * TB;
+    extern __shared__ __align__(16) unsigned long long smem[];
+    unsigned long long *s_sum = eval_sum_ptr<KC>(smem, TB);
+    double *s_w = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + eval_smem_bytes_c(KC, TB));
+    constexpr int XB = 8;
     const int t = threadIdx.x;
     const int K = A.K;
+    const bool w_resident = A.dm <= A.wchunk;
     if (t < KC) s_sum[t] = 0ull;
+    if (w_resident)
+        for (uint32_t i = t; i < A.dm * KC; i += TB) s_w[i] = __ldg(A.wt + i);
     __syncthreads();
     for (uint32_t tile = blockIdx.x; tile < P.nt; tile += gridDim.x) {
         const uint32_t doc0 = P.tile_doc_off[tile];
         const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
         const bool active = t < nd;
-        uint32_t pos = 0, qs = 0, qe = 0;
-        unsigned long long key[KC];
+        uint32_t pos = 0, qp = 0;
+        double tk[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) tk[k] = 0.0;
         if (active) {
             pos = P.pd_pos[doc0 + t];
-            const uint32_t qp = P.pd_q[doc0 + t];
-            qs = qp & 0xffffu;
-            qe = qp >> 16;
-            const float *__restrict__ xp = P.x + pos;
-            double tk[KC];
-#pragma unroll
-            for (int k = 0; k < KC; ++k) tk[k] = 0.0;
-#pragma unroll 4
-            for (uint32_t j = 0; j < A.dm; ++j) {
-                const double xv = (double)__ldg(xp + (size_t)j * P.ld);
-                const double *__restrict__ wj = A.wt + (size_t)j * KC;
-#pragma unroll
-                for (int k = 0; k < KC; ++k) tk[k] = __dadd_rn(tk[k], __dmul_rn(xv, __ldg(wj + k)));
-            }
-#pragma unroll
-            for (int k = 0; k < KC; ++k) key[k] = k < K ? score_key(tk[k], A.err) : 0ull;
-        } else {
-#pragma unroll
-            for (int k = 0; k < KC; ++k) key[k] = 0ull;
+            qp = P.pd_q[doc0 + t];
         }
-        rank_and_metric<KC>(P, tile, TB, t, active, qs, qe, pos, key, K, s_keys, s_sum, A.perq,
-                            A.err);
+        const float *__restrict__ xp = P.x + pos;
+        for (uint32_t j0 = 0; j0 < A.dm; j0 += A.wchunk) {
+            const uint32_t n = min(A.wchunk, A.dm - j0);
+            if (!w_resident) {
+                __syncthreads();  // the previous chunk (or tile) is done with s_w
+                for (uint32_t i = t; i < n * KC; i += TB) s_w[i] = __ldg(A.wt + (size_t)j0 * KC + i);
+                __syncthreads();
+            }
+            if (active) {
+                // XB feature values per document are requested before the previous XB are
+                // consumed, so every warp keeps XB 128-byte row segments in flight
+                const float *__restrict__ xj = xp + (size_t)j0 * P.ld;
+                float xn[XB];
+                if (n >= (uint32_t)XB) {
+#pragma unroll
+                    for (int u = 0; u < XB; ++u) xn[u] = ld_x(xj + (size_t)u * P.ld);
+                }
+                uint32_t j = 0;
+                for (; j + XB <= n; j += XB) {
+                    float xc[XB];
+#pragma unroll
+                    for (int u = 0; u < XB; ++u) xc[u] = xn[u];
+                    if (j + 2 * XB <= n) {
+#pragma unroll
+                        for (int u = 0; u < XB; ++u) xn[u] = ld_x(xj + (size_t)(j + XB + u) * P.ld);
+                    }
+#pragma unroll
+                    for (int u = 0; u < XB; ++u) {
+                        const double xv = (double)xc[u];
+                        const double *wj = s_w + (size_t)(j + u) * KC;
+#pragma unroll
+                        for (int k = 0; k < KC; k += 2) {
+                            const double2 w2 = *reinterpret_cast<const double2 *>(wj + k);
+                            tk[k] = __dadd_rn(tk[k], __dmul_rn(xv, w2.x));
+                            tk[k + 1] = __dadd_rn(tk[k + 1], __dmul_rn(xv, w2.y));
+                        }
+                    }
+                }
+                if (j < n) {
+                    float xc[XB];
+#pragma unroll
+                    for (int u = 0; u < XB; ++u)
+                        xc[u] = j + u < n ? ld_x(xj + (size_t)(j + u) * P.ld) : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < XB; ++u) {
+                        if (j + u < n) {
+                            const double xv = (double)xc[u];
+                            const double *wj = s_w + (size_t)(j + u) * KC;
+#pragma unroll
+                            for (int k = 0; k < KC; k += 2) {
+                                const double2 w2 = *reinterpret_cast<const double2 *>(wj + k);
+                                tk[k] = __dadd_rn(tk[k], __dmul_rn(xv, w2.x));
+                                tk[k + 1] = __dadd_rn(tk[k + 1], __dmul_rn(xv, w2.y));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        rank_and_metric<KC>(P, tile, TB, t, active, qp, pos, tk, K, smem, A.perq, A.err);
     }
     if (t < K) atomicAdd((unsigned long long *)(A.sums + t), s_sum[t]);
 }
@@ -303,9 +420,8 @@ __global__ void __launch_bounds__(TB) linear_batch_kernel(PlanView P, BatchArgs 
 template <int TB>
 __global__ void __launch_bounds__(TB) scores_eval_kernel(PlanView P, const double *__restrict__ scores,
                                                          long long *sums, double *perq, int *err) {
-    extern __shared__ unsigned long long smem[];
-    unsigned long long *s_keys = smem;
-    unsigned long long *s_sum = smem + TB;
+    extern __shared__ __align__(16) unsigned long long smem[];
+    unsigned long long *s_sum = eval_sum_ptr<1>(smem, TB);
     const int t = threadIdx.x;
     if (t == 0) s_sum[0] = 0ull;
     __syncthreads();
@@ -313,16 +429,14 @@ __global__ void __launch_bounds__(TB) scores_eval_kernel(PlanView P, const doubl
         const uint32_t doc0 = P.tile_doc_off[tile];
         const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
         const bool active = t < nd;
-        uint32_t pos = 0, qs = 0, qe = 0;
-        unsigned long long key[1] = {0ull};
+        uint32_t pos = 0, qp = 0;
+        double sc[1] = {0.0};
         if (active) {
             pos = P.pd_pos[doc0 + t];
-            const uint32_t qp = P.pd_q[doc0 + t];
-            qs = qp & 0xffffu;
-            qe = qp >> 16;
-            key[0] = score_key(__ldg(scores + pos), err);
+            qp = P.pd_q[doc0 + t];
+            sc[0] = __ldg(scores + pos);
         }
-        rank_and_metric<1>(P, tile, TB, t, active, qs, qe, pos, key, 1, s_keys, s_sum, perq, err);
+        rank_and_metric<1>(P, tile, TB, t, active, qp, pos, sc, 1, smem, perq, err);
     }
     if (t == 0) atomicAdd((unsigned long long *)sums, s_sum[0]);
 }
@@ -430,7 +544,7 @@ __global__ void plan_norms_kernel(PlanView P, const uint8_t *__restrict__ ov_pre
     out[pq] = norm;
 }
 
-size_t eval_smem_bytes(int kc, int tb) { return sizeof(unsigned long long) * ((size_t)kc * tb + kc); }
+size_t eval_smem_bytes(int kc, int tb) { return eval_smem_bytes_c(kc, tb); }
 
 template <typename KernelT>
 int grid_for(KernelT kernel, int tb, size_t smem, int sm_count, uint32_t nt, uint32_t split,
@@ -499,8 +613,12 @@ int launch_sweep(fr_dev_plan *pl, int kc, int tb, uint32_t n_sweeps, const Sweep
     return 0;
 }
 
-int launch_batch(fr_dev_plan *pl, int kc, int tb, const BatchArgs &args, cudaStream_t stream) {
-    const size_t smem = eval_smem_bytes(kc, tb);
+int launch_batch(fr_dev_plan *pl, int kc, int tb, const BatchArgs &args_in, cudaStream_t stream) {
+    // the weights of up to 32 KB worth of features are staged in shared memory at a time
+    BatchArgs args = args_in;
+    args.wchunk = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(args.dm, 1),
+                                                           32768u / (uint32_t)(kc * sizeof(double))));
+    const size_t smem = eval_smem_bytes(kc, tb) + (size_t)args.wchunk * kc * sizeof(double);
     PlanView pv = pl->view();
     DISPATCH_ALL({
         uint32_t gx = 1;
