@@ -70,17 +70,6 @@ __device__ __forceinline__ unsigned long long *eval_sum_ptr(unsigned long long *
     return smem + (size_t)eval_srow(KC) * tb + (size_t)KC * tb + tb;
 }
 
-// cnt += (sj > my) || (sj == my && before): the document at j outranks mine
-// (evaluators.rs:33-49: score descending; on equal scores the earlier local position wins,
-// local order being the reference's gain-ascending / id-ascending tie-break).  DSETP compares
-// -0.0 == +0.0 like NotNan does (evaluators.rs:36); NaN scores are reported before ranking.
-__device__ __forceinline__ void count_outranks(unsigned &cnt, double sj, double my, unsigned before) {
-    asm("{ .reg .pred p, q; setp.ne.u32 q, %3, 0; setp.eq.and.f64 p, %1, %2, q;"
-        " setp.gt.or.f64 p, %1, %2, p; @p add.u32 %0, %0, 1; }"
-        : "+r"(cnt)
-        : "d"(sj), "d"(my), "r"(before));
-}
-
 // Rank one tile for up to KC candidates and fold the per-query metric into s_sum.
 //
 // sc[k] is the score of this thread's local document under candidate k.  Only documents whose
@@ -877,11 +866,32 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
             pos.resize(ds->q_len[q]);
             for (uint32_t k = 0; k < ds->q_len[q]; ++k) pos[k] = ds->q_start[q] + k;
         }
-        if (pos.size() > (size_t)kMaxTile) {
+    }
+    // Which lists are tiled.  Tiles hold whole queries; the batched sweep takes tiles of up to
+    // kFastTile documents, the exact-order kernels up to kMaxTile.  A few long lists must not push
+    // a whole dataset off the batched sweep, so when at most a quarter of the documents sit in
+    // lists longer than kFastTile those lists are ranked from HBM (long_queries.cu) and the rest is
+    // tiled for the batched sweep; otherwise only lists beyond kMaxTile leave the tiles.
+    uint32_t tile_cap = (uint32_t)kMaxTile;
+    {
+        uint64_t docs = 0, docs_over = 0;
+        for (const auto &pos : qpos) {
+            docs += pos.size();
+            if (pos.size() > (size_t)kFastTile) docs_over += pos.size();
+        }
+        if (docs_over > 0 && docs_over * 4 <= docs) tile_cap = (uint32_t)kFastTile;
+        if (const char *env = getenv("FASTRANK_TILE_CAP")) {  // test knob: 32 .. kMaxTile
+            const int v = atoi(env);
+            if (v >= 32 && v <= kMaxTile) tile_cap = (uint32_t)v;
+        }
+    }
+    for (uint32_t v = 0; v < desc->n_queries; ++v) {
+        const uint32_t len = (uint32_t)qpos[v].size();
+        if (len > tile_cap) {
             long_views.push_back(v);  // ranked from HBM by long_queries.cu
-            longest = std::max<uint32_t>(longest, (uint32_t)pos.size());
+            longest = std::max(longest, len);
         } else {
-            max_len = std::max<uint32_t>(max_len, (uint32_t)pos.size());
+            max_len = std::max(max_len, len);
         }
     }
     pl->max_len = max_len;
@@ -899,7 +909,7 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
     };
     for (uint32_t v = 0; v < desc->n_queries; ++v) {
         const uint32_t len = (uint32_t)qpos[v].size();
-        if (len > (uint32_t)kMaxTile) continue;
+        if (len > tile_cap) continue;
         if (cur_docs + len > (uint32_t)tb && cur_docs > 0) close_tile();
         const uint32_t start = cur_docs;
         pq_local.push_back(start | (len << 16));
@@ -946,10 +956,6 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
     }
     if (build_fast_plan(pl.get(), tile_q_off, pq_local, pq_doc0, pd_pos)) return 1;
     if (build_long_plan(pl.get(), qpos, long_views, desc)) return 1;
-    if (!long_views.empty()) {
-        pl->fast.ok = false;
-        pl->fast.why = "a query has more than 1024 documents";
-    }
     CU(cudaStreamSynchronize(s));
     pl->nq_global = pl->nq_view;
     *out = pl.release();

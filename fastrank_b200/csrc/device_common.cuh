@@ -82,7 +82,21 @@ struct PinnedBuf {
     }
 };
 
-constexpr int kMaxTile = 1024;
+constexpr int kMaxTile = 1024;  // largest tile of the exact-order kernels
+constexpr int kFastTile = 512;  // largest tile of the batched sweep (sweep_fast.cu)
+#ifdef __CUDACC__
+// cnt += (sj > my) || (sj == my && before): the document at j outranks mine
+// (evaluators.rs:33-49: score descending; on equal scores the earlier local position wins,
+// local order being the reference's gain-ascending / id-ascending tie-break).  DSETP compares
+// -0.0 == +0.0 like NotNan does (evaluators.rs:36); NaN scores are reported before ranking.
+__device__ __forceinline__ void count_outranks(unsigned &cnt, double sj, double my, unsigned before) {
+    asm("{ .reg .pred p, q; setp.ne.u32 q, %3, 0; setp.eq.and.f64 p, %1, %2, q;"
+        " setp.gt.or.f64 p, %1, %2, p; @p add.u32 %0, %0, 1; }"
+        : "+r"(cnt)
+        : "d"(sj), "d"(my), "r"(before));
+}
+#endif
+
 constexpr double kFxScale = 1099511627776.0; /* 2^FR_FX_BITS */
 static_assert(FR_FX_BITS == 40, "kFxScale must match FR_FX_BITS");
 

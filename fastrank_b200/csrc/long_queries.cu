@@ -1,19 +1,23 @@
-// long_queries.cu -- queries longer than the largest tile (1024 documents).
+// long_queries.cu -- queries that are not tiled: longer than the largest tile (1024 documents
+// for the exact-order kernels; 512 when the plan keeps the rest of the dataset on the batched
+// sweep, see fr_dev_plan_create).
 //
 // The tile kernels rank a whole query inside one CTA's shared memory; a query that does not fit
 // (MSLR-WEB30K has lists of ~1.2k documents, the reference sorts lists of any length,
-// evaluators.rs:206-221) takes this path instead: scores go to a scratch array in HBM, one CTA
-// per (query, candidate) ranks by counting straight from L2, metric terms are scattered to their
-// rank and folded in rank order by one thread -- the same arithmetic, in the same order, as
-// rank_and_metric in device.cu, so results are bit-identical to the oracle here too.  It is a
-// correctness path (O(len^2) global loads per list), not a tuned one: long lists are rare.
+// evaluators.rs:206-221) takes this path instead: scores go to a scratch array in HBM (exact
+// left-to-right dot products, 8 candidates per read of a feature value), one CTA per
+// (query, candidate) stages the list's scores in shared memory and ranks its contributing
+// documents by counting, metric terms are scattered to their rank and folded in rank order by
+// one thread -- the same arithmetic, in the same order, as rank_and_metric in device.cu, so
+// results are bit-identical to the oracle here too.  O(len^2) compares per (list, candidate).
 #include "device_common.cuh"
 
 namespace {
 
 constexpr double kFxLong = 1099511627776.0;
 static_assert(FR_FX_BITS == 40, "kFxLong must match FR_FX_BITS");
-constexpr int kLongChunk = 16;  // candidates per pass (bounds the scratch arrays)
+constexpr int kLongChunk = 64;  // candidates per pass (bounds the scratch arrays)
+constexpr int kLongSmem = 4096;  // list length whose scores are staged in shared memory
 
 struct LongView {
     const uint32_t *lq_off;   // n_long + 1, into ld_pos
@@ -23,31 +27,47 @@ struct LongView {
     uint32_t n_docs;
 };
 
-// dense_dataset.rs:67-76 for documents of long queries: scores[k][d], left-to-right f64 dot
+// dense_dataset.rs:67-76 for documents of long queries: scores[k][d], left-to-right f64 dot.
+// One thread scores one document for kLongKB candidates, so a feature value is read once per
+// kLongKB candidates; the loads of 8 features are issued before any of them is consumed.
+constexpr int kLongKB = 8;
 __global__ void long_linear_scores_kernel(const float *__restrict__ x, size_t ld, uint32_t dm,
                                           LongView L, const double *__restrict__ w, uint32_t wlen,
-                                          double *__restrict__ scores) {
+                                          uint32_t nc, double *__restrict__ scores) {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= L.n_docs) return;
+    const uint32_t k0 = blockIdx.y * kLongKB;
     const float *__restrict__ xp = x + L.ld_pos[d];
-    const double *__restrict__ wk = w + (size_t)blockIdx.y * wlen;
-    double acc = 0.0;
-    for (uint32_t j = 0; j < dm; ++j)
-        acc = __dadd_rn(acc, __dmul_rn((double)__ldg(xp + (size_t)j * ld), __ldg(wk + j)));
-    scores[(size_t)blockIdx.y * L.n_docs + d] = acc;
+    const double *wk[kLongKB];
+    double acc[kLongKB];
+#pragma unroll
+    for (int k = 0; k < kLongKB; ++k) {
+        wk[k] = w + (size_t)min(k0 + k, nc - 1) * wlen;  // rows past nc repeat the last one, unused
+        acc[k] = 0.0;
+    }
+    for (uint32_t j0 = 0; j0 < dm; j0 += 8) {
+        float xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xv[u] = j0 + u < dm ? __ldg(xp + (size_t)(j0 + u) * ld) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (j0 + u < dm) {
+                const double xd = (double)xv[u];
+#pragma unroll
+                for (int k = 0; k < kLongKB; ++k)
+                    acc[k] = __dadd_rn(acc[k], __dmul_rn(xd, __ldg(wk[k] + j0 + u)));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kLongKB; ++k)
+        if (k0 + k < nc) scores[(size_t)(k0 + k) * L.n_docs + d] = acc[k];
 }
 
 __global__ void long_gather_scores_kernel(LongView L, const double *__restrict__ scores_pos,
                                           double *__restrict__ scores) {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d < L.n_docs) scores[d] = scores_pos[L.ld_pos[d]];
-}
-
-__device__ __forceinline__ unsigned long long long_key(double s) {
-    long long b = __double_as_longlong(s);
-    if ((b << 1) == 0) b = 0;  // -0.0 == +0.0 (evaluators.rs:36)
-    const unsigned long long u = (unsigned long long)b;
-    return b < 0 ? ~u : (u | 0x8000000000000000ull);
 }
 
 __global__ void __launch_bounds__(256) long_rank_kernel(PlanView P, LongView L, const double *__restrict__ scores,
@@ -58,24 +78,39 @@ __global__ void __launch_bounds__(256) long_rank_kernel(PlanView P, LongView L, 
     const uint32_t base = L.lq_off[q], len = L.lq_off[q + 1] - base;
     const double *__restrict__ sc = scores + (size_t)k * L.n_docs + base;
     double *sl = slots + (size_t)k * L.n_docs + base;
+    // the list's scores are staged in shared memory when they fit, else read through L1
+    __shared__ double s_sc[kLongSmem];
+    const bool staged = len <= (uint32_t)kLongSmem;
     for (uint32_t t = threadIdx.x; t < len; t += blockDim.x) {
         const double st = sc[t];
         if (st != st) atomicOr(err, ERR_NAN_SCORE);
-        const unsigned long long kt = long_key(st);
-        uint32_t cnt = 0;
-        for (uint32_t j = 0; j < len; ++j) {
-            const unsigned long long kj = long_key(__ldg(sc + j));
-            cnt += (kj > kt) | ((kj == kt) & (j < t));
-        }
+        if (staged) s_sc[t] = st;
+        sl[t] = 0.0;
+    }
+    __syncthreads();
+    const double *__restrict__ src = staged ? s_sc : sc;
+    // only documents that can contribute are ranked (local order is gain-ascending, so they are
+    // the tail of the list and whole warps agree)
+    for (uint32_t t = threadIdx.x; t < len; t += blockDim.x) {
         const uint32_t pos = L.ld_pos[base + t];
-        double payload;
+        double ge = 0.0;
+        bool contrib;
         if (P.metric == FR_METRIC_NDCG) {
-            const double ge = P.gexp[pos];
-            payload = ((int)cnt < P.depth && ge != 0.0) ? ge / P.lg2[cnt] : 0.0;  // evaluators.rs:265-270
+            ge = P.gexp[pos];
+            contrib = ge != 0.0;
         } else {
-            payload = P.gain[pos] > 0.0f ? 1.0 : 0.0;
+            contrib = P.gain[pos] > 0.0f;
         }
-        sl[cnt] = payload;
+        if (!contrib) continue;
+        const double st = src[t];
+        unsigned cnt = 0;
+#pragma unroll 4
+        for (uint32_t j = 0; j < len; ++j) count_outranks(cnt, src[j], st, j < t ? 1u : 0u);
+        if (P.metric == FR_METRIC_NDCG) {
+            if ((int)cnt < P.depth) sl[cnt] = ge / P.lg2[cnt];  // evaluators.rs:265-270
+        } else {
+            sl[cnt] = 1.0;
+        }
     }
     __threadfence_block();
     __syncthreads();
@@ -206,8 +241,8 @@ int eval_long_linear(fr_dev_plan *pl, const double *w_host, size_t wlen, size_t 
         const uint32_t nc = (uint32_t)std::min<size_t>(kLongChunk, n_vec - c0);
         CU(cudaMemcpyAsync(lp.w.p, w_host + c0 * wlen, sizeof(double) * nc * wlen, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(lp.out_idx.p, out_index + c0, sizeof(uint32_t) * nc, cudaMemcpyHostToDevice, s));
-        long_linear_scores_kernel<<<dim3((lp.n_docs + 127) / 128, nc), 128, 0, s>>>(
-            ds->x.p, ds->ld, dm, long_view(pl), lp.w.p, (uint32_t)wlen, lp.scores.p);
+        long_linear_scores_kernel<<<dim3((lp.n_docs + 127) / 128, (nc + kLongKB - 1) / kLongKB), 128, 0, s>>>(
+            ds->x.p, ds->ld, dm, long_view(pl), lp.w.p, (uint32_t)wlen, nc, lp.scores.p);
         LAUNCHED();
         CU(cudaGetLastError());
         if (rank_chunk(pl, nc, lp.out_idx.p, sums_dev, perq_dev, err_dev, s)) return 1;

@@ -104,6 +104,10 @@ template <>
 struct SlotType<256> {
     typedef uint16_t type;
 };
+template <>
+struct SlotType<512> {
+    typedef uint16_t type;
+};
 
 struct SmemLayout {
     size_t score, sum, tbl, gexp, slot0, slot1, tasks, cls, rowsw, misc, w, total;
@@ -180,7 +184,7 @@ __device__ __forceinline__ void rank_task(const double *__restrict__ myrow, int 
 }
 
 template <int TB, int TD, bool WS>
-__global__ void __launch_bounds__(TB, (TB == 128 ? (WS ? 4 : 5) : 2))
+__global__ void __launch_bounds__(TB, (TB == 128 ? (WS ? 4 : 5) : (TB == 256 ? 2 : 1)))
 sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename SlotType<TB>::type slot_t;
@@ -572,8 +576,8 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
     FastPlan &fp = pl->fast;
     fr_dev_dataset *ds = pl->ds;
     fp.ok = false;
-    if (pl->tb > 256) {
-        fp.why = "a query has more than 256 documents";
+    if (pl->tb > kFastTile) {
+        fp.why = "too many documents sit in queries of more than 512 documents";
         return 0;
     }
     int td = 8;
@@ -726,6 +730,24 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
     CU(cudaMemsetAsync(fp.out_dev.p, 0, out_bytes, s));
     if (out_per_query)
         CU(cudaMemsetAsync(pl->perq_dev.p, 0, sizeof(double) * total * (size_t)pl->nq_view, s));
+    if (pl->lng.n_long > 0) {
+        // lists that do not fit a tile: every candidate as a full weight vector, scored and ranked
+        // from HBM (long_queries.cu).  Their sums land in sums_dev BEFORE the tile kernel runs, so
+        // the fused cross-GPU reduction in its tail covers them as well.
+        std::vector<double> full;
+        std::vector<uint32_t> out_index;
+        for (size_t r = 0; r < n_sweeps; ++r) {
+            for (uint32_t k = 0; k < n_cand[r]; ++k) {
+                full.insert(full.end(), base_w + r * wlen, base_w + (r + 1) * wlen);
+                if (fid[r] < wlen) full[full.size() - wlen + fid[r]] = cand_w[r * cand_stride + k];
+                out_index.push_back((uint32_t)(r * cand_stride + k));
+            }
+        }
+        if (eval_long_linear(pl, full.data(), wlen, out_index.size(), out_index.data(), sums_dev,
+                             out_per_query ? pl->perq_dev.p : nullptr, err_dev, s))
+            return 1;
+        CU(cudaStreamSynchronize(s));  // `full` is staged from pageable memory
+    }
     bool first_pass = true;
     for (;;) {
         if (!first_pass) CU(cudaStreamSynchronize(s));  // the staging blob is about to be rewritten
@@ -802,9 +824,12 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
             else
                 rc = fp.td == 8 ? launch_fast<128, 8, false>(pl, a, n_groups, s)
                                 : launch_fast<128, 4, false>(pl, a, n_groups, s);
-        } else {
+        } else if (pl->tb == 256) {
             rc = fp.td == 8 ? launch_fast<256, 8, false>(pl, a, n_groups, s)
                             : launch_fast<256, 4, false>(pl, a, n_groups, s);
+        } else {
+            rc = fp.td == 8 ? launch_fast<512, 8, false>(pl, a, n_groups, s)
+                            : launch_fast<512, 4, false>(pl, a, n_groups, s);
         }
         if (rc) return 1;
     }

@@ -138,10 +138,11 @@ def test_ragged_queries_and_length_limit(oracle):
             _check(oracle, ods, X, plan, name, base, fids, cands, exact=True)
     finally:
         dev.close()
-    # one document more than the kernel ranks per query: the entry point must refuse, loudly
-    qid2 = np.concatenate([qid, np.full(257, 999)]).astype(np.int64)
-    X2 = np.concatenate([X, rng.normal(size=(257, 7)).astype(np.float32)])
-    y2 = np.concatenate([y, rng.integers(0, 3, 257).astype(np.float64)])
+    # when more than a quarter of the documents sit in lists beyond the largest sweep tile the
+    # plan stays on the exact-order kernels, and the batched entry point must refuse, loudly
+    qid2 = np.concatenate([qid, np.full(513, 999)]).astype(np.int64)
+    X2 = np.concatenate([X, rng.normal(size=(513, 7)).astype(np.float32)])
+    y2 = np.concatenate([y, rng.integers(0, 3, 513).astype(np.float64)])
     qidx, nq = dense_qidx(qid2)
     dev2 = DevDataset(X2, y2.astype(np.float32), qidx, nq)
     try:
@@ -258,3 +259,92 @@ def test_more_rows_than_one_pass_holds(oracle):
                 assert abs(int(fast[r, k]) - fx_sum(exp)) / FX / 90 < 1e-9
     finally:
         dev.close()
+
+
+def _ragged(rng, lens, d=6, integer=False):
+    qid = np.concatenate([np.full(l, 3 + 2 * i) for i, l in enumerate(lens)]).astype(np.int64)
+    n = len(qid)
+    if integer:
+        X = rng.integers(-3, 4, size=(n, d)).astype(np.float32)
+    else:
+        X = rng.normal(size=(n, d)).astype(np.float32)
+        X[:, 2] = rng.integers(0, 4, n)      # ties
+    y = (rng.integers(0, 5, n) * (rng.random(n) < 0.5)).astype(np.float64)
+    return X, y, qid
+
+
+@pytest.mark.parametrize("integer", [True, False])
+def test_tiles_of_up_to_512_documents(oracle, integer):
+    """Lists of 257 .. 512 documents stay on the batched sweep (512-document tiles, one CTA per
+    SM); with exact arithmetic the results are bit-identical to the oracle."""
+    rng = np.random.default_rng(81)
+    lens = [500, 30, 300, 12, 512, 64, 257, 5, 130, 511, 1, 400]
+    X, y, qid = _ragged(rng, lens, integer=integer)
+    _, _, _, ods, dev = _mk(oracle, 0, 0, 0, 0, X=X, y=y, qid=qid)
+    try:
+        for name, metric, depth in (("ndcg@10", 0, 10), ("map", 1, -1), ("mrr", 2, -1), ("ndcg", 0, -1)):
+            plan = dev.plan(metric, depth)
+            assert dev.lib.fr_dev_plan_has_fast_sweep(plan.ptr) == 1
+            if integer:
+                base = rng.integers(-4, 5, size=(3, 6)).astype(np.float64) / 8.0
+                cands = [[float(v) / 4.0 for v in rng.integers(-8, 9, 40)] for _ in range(3)]
+            else:
+                base = rng.normal(size=(3, 6))
+                cands = [_line(base[r, f], 40) for r, f in enumerate([0, 2, 5])]
+            _check(oracle, ods, X, plan, name, base, [0, 2, 5], cands, exact=integer, max_flip_frac=0.02)
+    finally:
+        dev.close()
+
+
+def test_long_lists_next_to_the_batched_sweep(oracle):
+    """A few lists longer than the largest sweep tile (600 .. 2000 documents, under a quarter of
+    the documents) must not push the dataset off the batched sweep: they are ranked from HBM,
+    everything else in tiles, one call returns both."""
+    rng = np.random.default_rng(82)
+    lens = [int(v) for v in rng.integers(1, 120, 260)]
+    for at, l in ((7, 600), (100, 1100), (259, 2000)):
+        lens.insert(at, l)
+    X, y, qid = _ragged(rng, lens, integer=True)
+    assert sum(l for l in lens if l > 512) * 4 <= len(qid)
+    _, _, _, ods, dev = _mk(oracle, 0, 0, 0, 0, X=X, y=y, qid=qid)
+    try:
+        for name, metric, depth in (("ndcg@10", 0, 10), ("map", 1, -1), ("mrr", 2, -1)):
+            plan = dev.plan(metric, depth)
+            assert dev.lib.fr_dev_plan_has_fast_sweep(plan.ptr) == 1
+            base = rng.integers(-4, 5, size=(4, 6)).astype(np.float64) / 8.0
+            cands = [[float(v) / 4.0 for v in rng.integers(-8, 9, 70)] for _ in range(4)]  # > one scratch chunk
+            _check(oracle, ods, X, plan, name, base, [1, 2, 3, 9], cands, exact=True)
+            # the exact-order entry point and evaluate_mean see the same split
+            sums = plan.coord_sweeps(base[:2], [1, 2], [cands[0][:5], cands[1][:5]])
+            fast = plan.coord_sweeps(base[:2], [1, 2], [cands[0][:5], cands[1][:5]], fast=True)
+            assert np.array_equal(sums, fast)
+    finally:
+        dev.close()
+
+
+def test_tile_cap_knob_and_training_with_untiled_lists(oracle, monkeypatch):
+    """FASTRANK_TILE_CAP moves the tiled / untiled boundary: a model trained with most lists
+    untiled (cap 32) is the model trained with everything tiled."""
+    import fastrank_b200 as fr
+
+    rng = np.random.default_rng(83)
+    lens = [int(v) for v in rng.integers(1, 90, 60)]
+    X, y, qid = _ragged(rng, lens, integer=True)
+    req = fr.TrainRequest.coordinate_ascent()
+    req.measure = "ndcg@5"
+    req.params.num_restarts, req.params.seed, req.params.quiet = 2, 5, True
+    got = {}
+    for cap in (None, "32"):
+        if cap is None:
+            monkeypatch.delenv("FASTRANK_TILE_CAP", raising=False)
+        else:
+            monkeypatch.setenv("FASTRANK_TILE_CAP", cap)
+        ds = fr.CDataset.from_numpy(X, y, qid)
+        m = ds.train_model(req)
+        got[cap] = (m.to_dict()["Linear"]["weights"], fr.query_json("last_train_stats")["evals_consumed"],
+                    ds.evaluate_mean(m, "ndcg@5"))
+    assert got[None] == got["32"]
+    ods = oracle_dataset(oracle, X, y, qid)
+    res = oracle.coordinate_ascent(ods, "ndcg@5", num_restarts=2, seed=5)
+    assert got["32"][1] == res["n_evals"]
+    assert np.allclose(got["32"][0], res["weights"], rtol=0, atol=1e-12)
