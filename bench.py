@@ -50,8 +50,10 @@ DEPTH = 10
 METRIC = "CA NDCG@10 evaluations/sec on 1M x 136 DenseDataset"
 UNIT = "evals/s"
 WORKLOAD = "synthetic 1M docs x 136 features x 30k queries, coordinate_ascent 8 restarts, ndcg@10"
-if (N_DOCS, N_QUERIES) != (1_000_000, 30_000):
-    WORKLOAD = "synthetic %d docs x 136 features x %d queries, coordinate_ascent 8 restarts, ndcg@10" % (N_DOCS, N_QUERIES)
+LONG_TAIL = os.environ.get("FASTRANK_BENCH_TAIL", "") == "1"  # side experiment: MSLR-like list lengths
+if (N_DOCS, N_QUERIES) != (1_000_000, 30_000) or LONG_TAIL:
+    WORKLOAD = "synthetic %d docs x 136 features x %d queries%s, coordinate_ascent 8 restarts, ndcg@10" % (
+        N_DOCS, N_QUERIES, " (log-normal list lengths, up to 1300 documents)" if LONG_TAIL else "")
 
 
 def log(*a):
@@ -63,6 +65,16 @@ def make_data(n=N_DOCS, d=N_FEAT, q=N_QUERIES):
 
     t = time.time()
     X, y, qid = synth(n, d, q)
+    if LONG_TAIL:
+        # list lengths like a web collection's: log-normal around n / q, a tail of lists of more
+        # than a thousand documents (MSLR-WEB30K: mean 120, maximum 1251)
+        rng = np.random.default_rng(7)
+        sigma = 0.8
+        lens = rng.lognormal(np.log(n / q) - sigma * sigma / 2, sigma, size=q)
+        lens = np.clip(np.rint(lens), 1, 1300).astype(np.int64)
+        qid = np.repeat(np.arange(q, dtype=np.int64), lens)
+        rest = max(n - len(qid), 0)  # what the draw left over goes into lists of the mean length
+        qid = np.concatenate([qid, q + np.arange(rest, dtype=np.int64) // max(n // q, 1)])[:n]
     log("[bench] synthetic data %dx%d, %d queries in %.1fs" % (n, d, len(np.unique(qid)), time.time() - t))
     return X, y, qid
 
@@ -264,6 +276,7 @@ def run_ours(args, rank, world, local_rank):
         if lib.fr_dev_plan_set_comm(plan.ptr, comm.ptr):
             raise RuntimeError("fr_dev_plan_set_comm failed")
 
+    plan_layout = (int(lib.fr_dev_plan_tile_documents(plan.ptr)), int(lib.fr_dev_plan_untiled_queries(plan.ptr)))
     # the (tiny) inputs of every step are laid out before the clock starts: what is timed is the
     # C-ABI call -- staging of weights and candidates, the kernel, the all-reduce, the read-back
     # train_model submits direction +1 together with directions 0 / -1 (one launch, 8 x 51
@@ -316,7 +329,8 @@ def run_ours(args, rank, world, local_rank):
     else:
         bytes_per_launch = (n_local * d * 4 + n_local * 5 + nq_local * 16 + N_RESTARTS * d * 8
                             + EVALS_PER_STEP // launches_per_step * 16)
-        kname = "sweep_fast_kernel<128,8,true>"
+        tile = int(lib.fr_dev_plan_tile_documents(plan.ptr))
+        kname = "sweep_fast_kernel<%d,8,%s>" % (tile, "true" if tile == 128 else "false")
     avg_launch_ms = kern_ms / max(n_kern, 1)
     achieved = bytes_per_launch / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else 0.0
     peak, peak_src = measured_peak_gbs()
@@ -393,7 +407,8 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "evals_per_step": EVALS_PER_STEP,
                        "l2": "inputs (544 MB feature matrix per sweep) larger than the 126 MB L2",
                        "parallelism": "query-sharded x%d" % world if world > 1 else "single GPU",
-                       "wall_ms_per_step": wall_ms / max(args.steps, 1)},
+                       "wall_ms_per_step": wall_ms / max(args.steps, 1),
+                       "tile_documents": plan_layout[0], "untiled_queries": plan_layout[1]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }
         if cpu is not None:

@@ -969,6 +969,8 @@ void fr_dev_plan_destroy(fr_dev_plan *plan) {
 }
 
 uint64_t fr_dev_plan_global_queries(const fr_dev_plan *plan) { return plan ? plan->nq_global : 0; }
+uint32_t fr_dev_plan_tile_documents(const fr_dev_plan *plan) { return plan ? (uint32_t)plan->tb : 0; }
+uint32_t fr_dev_plan_untiled_queries(const fr_dev_plan *plan) { return plan ? plan->lng.n_long : 0; }
 
 int fr_dev_plan_set_comm(fr_dev_plan *plan, fr_dev_comm *comm) {
     if (!plan) return fail("fr_dev_plan_set_comm: NULL plan");

@@ -157,6 +157,11 @@ void fr_dev_plan_destroy(fr_dev_plan *plan);
  * query count across ranks. */
 int fr_dev_plan_set_comm(fr_dev_plan *plan, fr_dev_comm *comm);
 uint64_t fr_dev_plan_global_queries(const fr_dev_plan *plan);
+/* How the plan laid the view out: documents per tile (whole queries are packed into tiles of
+ * 128 .. 1024 documents, evaluators.rs:206-221 ranks one query at a time) and the number of
+ * local queries too long for a tile, which are ranked from HBM instead. */
+uint32_t fr_dev_plan_tile_documents(const fr_dev_plan *plan);
+uint32_t fr_dev_plan_untiled_queries(const fr_dev_plan *plan);
 
 /* evaluate_mean for C weight vectors in one pass over the matrix
  * (coordinate_ascent.rs:110 / evaluators.rs:173-224 with model.rs:47-51 scoring).
