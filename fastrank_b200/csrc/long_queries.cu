@@ -104,8 +104,14 @@ __global__ void __launch_bounds__(256) long_rank_kernel(PlanView P, LongView L, 
         if (!contrib) continue;
         const double st = src[t];
         unsigned cnt = 0;
+        // a document that `depth` others already outrank adds nothing to DCG@depth: stop counting
+        // (most documents of a long list leave after a few dozen compares)
+        const unsigned enough = P.metric == FR_METRIC_NDCG ? (unsigned)min((unsigned)P.depth, len) : len;
+        for (uint32_t j0 = 0; j0 < len && cnt < enough; j0 += 32) {
+            const uint32_t j1 = min(j0 + 32u, len);
 #pragma unroll 4
-        for (uint32_t j = 0; j < len; ++j) count_outranks(cnt, src[j], st, j < t ? 1u : 0u);
+            for (uint32_t j = j0; j < j1; ++j) count_outranks(cnt, src[j], st, j < t ? 1u : 0u);
+        }
         if (P.metric == FR_METRIC_NDCG) {
             if ((int)cnt < P.depth) sl[cnt] = ge / P.lg2[cnt];  // evaluators.rs:265-270
         } else {
