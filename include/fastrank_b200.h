@@ -126,8 +126,8 @@ int fr_dev_device_count(void);
  *   query_index n uint32    dense query number of each instance, in [0, n_queries)
  * Rows are regrouped by query and, inside a query, ordered by (gain asc, instance id asc) --
  * the reference's tie-break (evaluators.rs:33-49) -- so that ranking on the device is a
- * stable descending sort by score.  Queries may have any length: lists of up to 1024 documents
- * are ranked in shared memory, longer ones from HBM. */
+ * stable descending sort by score.  Queries may have any length: lists that fit a tile (up to
+ * 1024 documents) are ranked in shared memory, longer ones from HBM. */
 int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const float *gains,
                           const uint32_t *query_index, uint32_t n_queries, fr_dev_dataset **out);
 void fr_dev_dataset_destroy(fr_dev_dataset *ds);
@@ -189,14 +189,16 @@ int fr_dev_eval_coord_sweeps(fr_dev_plan *plan, size_t n_sweeps, const double *b
  * the reference's, so per-query values are bit-identical to the exact path whenever the ranking
  * is.  This is what train_model uses (FASTRANK_SWEEP=exact selects the entry point above
  * instead); it submits all three directions of a line search (1 + 2 * num_max_iterations
- * candidates per restart) in one call.  Requires queries of at most 256 documents
- * (fr_dev_plan_has_fast_sweep).  out_per_query: NULL or n_sweeps x cand_stride x n_queries
- * (view order). */
+ * candidates per restart) in one call.  Tiles of the batched sweep hold up to 512 documents;
+ * when at most a quarter of the view's documents sit in longer lists those lists are ranked from
+ * HBM next to the tiles (scored with the exact dot product) and the call serves the whole view,
+ * otherwise the plan stays on the exact-order kernels (fr_dev_plan_has_fast_sweep == 0).
+ * out_per_query: NULL or n_sweeps x cand_stride x n_queries (view order). */
 int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *plan, size_t n_sweeps, const double *base_w,
                                   size_t wlen, const uint32_t *fid, const double *cand_w,
                                   const uint32_t *n_cand, size_t cand_stride, int64_t *out_sum_fx,
                                   double *out_per_query);
-/* 1 when the batched sweep supports this plan (queries of at most 256 documents). */
+/* 1 when the batched sweep serves this plan (see above). */
 int fr_dev_plan_has_fast_sweep(const fr_dev_plan *plan);
 
 /* Flattened ModelEnum (model.rs:10-16).  `code` is a postfix program of 64-bit words; see
