@@ -215,6 +215,13 @@ __device__ __forceinline__ void rank_and_metric(const PlanView &P, uint32_t tile
     __syncthreads();
 }
 
+// X is read once per launch: keep it out of L1 (the per-document plan arrays stay there).
+__device__ __forceinline__ float ld_x(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 struct SweepArgs {
     const double *base_w;   // [n_sweeps][wlen]
     const uint32_t *fid;    // [n_sweeps]
@@ -260,24 +267,38 @@ __global__ void __launch_bounds__(TB) coord_sweep_kernel(PlanView P, SweepArgs A
             qp = P.pd_q[doc0 + t];
             const float *__restrict__ xp = P.x + pos;
             double acc = 0.0;
-            const uint32_t fsplit = f < dm ? f : dm;
-#pragma unroll 8
-            for (uint32_t j = 0; j < fsplit; ++j)
-                acc = __dadd_rn(acc, __dmul_rn((double)__ldg(xp + (size_t)j * P.ld), __ldg(w + j)));
-            if (f < dm) {
-                const double xf = (double)__ldg(xp + (size_t)f * P.ld);
+            // features in blocks of 8: the loads of a block are issued together (one load in
+            // flight per warp otherwise), then consumed in the reference's order
+            for (uint32_t j0 = 0; j0 < dm; j0 += 8) {
+                float xv[8];
+                double wv[8];
 #pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    const double wk = k < K ? __ldg(cw + k) : 0.0;
-                    tk[k] = __dadd_rn(acc, __dmul_rn(xf, wk));
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t j = j0 + u < dm ? j0 + u : dm - 1;
+                    xv[u] = ld_x(xp + (size_t)j * P.ld);
+                    wv[u] = __ldg(w + j);
                 }
-#pragma unroll 4
-                for (uint32_t j = f + 1; j < dm; ++j) {
-                    const double p = __dmul_rn((double)__ldg(xp + (size_t)j * P.ld), __ldg(w + j));
 #pragma unroll
-                    for (int k = 0; k < KC; ++k) tk[k] = __dadd_rn(tk[k], p);
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t j = j0 + u;
+                    if (j >= dm) break;
+                    const double xd = (double)xv[u];
+                    if (j < f) {
+                        acc = __dadd_rn(acc, __dmul_rn(xd, wv[u]));
+                    } else if (j == f) {
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            const double wk = k < K ? __ldg(cw + k) : 0.0;
+                            tk[k] = __dadd_rn(acc, __dmul_rn(xd, wk));
+                        }
+                    } else {
+                        const double p = __dmul_rn(xd, wv[u]);
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) tk[k] = __dadd_rn(tk[k], p);
+                    }
                 }
-            } else {
+            }
+            if (f >= dm) {
 #pragma unroll
                 for (int k = 0; k < KC; ++k) tk[k] = acc;
             }
@@ -298,13 +319,6 @@ struct BatchArgs {
     int K;
     int *err;
 };
-
-// X is read once per launch: keep it out of L1 (the per-document plan arrays stay there).
-__device__ __forceinline__ float ld_x(const float *p) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
 
 __host__ __device__ constexpr size_t eval_smem_bytes_c(int kc, int tb) {
     return ((8 * eval_words(kc, tb) + 4 * (size_t)tb + 4 * 32 + 2 * (size_t)tb) + 15) / 16 * 16;
