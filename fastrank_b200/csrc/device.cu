@@ -158,14 +158,16 @@ __device__ __forceinline__ void rank_and_metric(const PlanView &P, uint32_t tile
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 // compute_dcg, evaluators.rs:265-270: (2^gain - 1) / log2(i + 2)
-                if (k < K && (int)cnt[k] < P.depth)
+                // (a NaN score compares false with everything: it is reported above and must
+                // not land on the slot of the document that really holds rank cnt)
+                if (k < K && (int)cnt[k] < P.depth && my[k] == my[k])
                     s_slot[(size_t)(qs + cnt[k]) * KC + k] =
                         (unsigned long long)__double_as_longlong(ge / __ldg(P.lg2 + cnt[k]));
             }
         } else {
 #pragma unroll
             for (int k = 0; k < KC; ++k)
-                if (k < K) s_slot[(size_t)(qs + cnt[k]) * KC + k] = 1ull;
+                if (k < K && my[k] == my[k]) s_slot[(size_t)(qs + cnt[k]) * KC + k] = 1ull;
         }
     }
     __syncthreads();

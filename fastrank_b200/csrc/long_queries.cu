@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(256) long_rank_kernel(PlanView P, LongView L, 
 #pragma unroll 4
             for (uint32_t j = j0; j < j1; ++j) count_outranks(cnt, src[j], st, j < t ? 1u : 0u);
         }
+        if (st != st) continue;  // NaN: reported above, must not take another document's slot
         if (P.metric == FR_METRIC_NDCG) {
             if ((int)cnt < P.depth) sl[cnt] = ge / P.lg2[cnt];  // evaluators.rs:265-270
         } else {
