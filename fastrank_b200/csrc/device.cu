@@ -993,9 +993,16 @@ int fr_dev_plan_set_comm(fr_dev_plan *plan, fr_dev_comm *comm) {
     plan->comm = comm;
     plan->nq_global = plan->nq_view;
     if (comm && comm->world > 1) {
-        uint64_t v = plan->nq_view;
-        if (fr_dev_comm_allreduce_u64(comm, &v, 1)) return 1;
-        plan->nq_global = v;
+        // ranks agree on the query count and on WHICH sweep entry point serves the job: a rank
+        // whose shard cannot use the batched sweep takes every rank to the exact-order kernels
+        // (the two reduce differently, so a mixed job would wait on itself)
+        uint64_t v[2] = {plan->nq_view, plan->fast.ok ? 0u : 1u};
+        if (fr_dev_comm_allreduce_u64(comm, v, 2)) return 1;
+        plan->nq_global = v[0];
+        if (v[1] > 0 && plan->fast.ok) {
+            plan->fast.ok = false;
+            plan->fast.why = "the shard of another rank cannot use the batched sweep";
+        }
     }
     return 0;
 }

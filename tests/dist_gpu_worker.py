@@ -33,6 +33,36 @@ def many_rows():
     return base, fids, cands
 
 
+def long_list_data(kind):
+    """Integer features (exact arithmetic: every schedule gives the same bits) and lists too long
+    for a sweep tile.  "hybrid": one 700-document list per rank among short ones, so both ranks
+    rank it from HBM next to the batched sweep.  "mixed": the long lists dominate the LAST rank's
+    shard only -- that rank cannot use the batched sweep, and the ranks have to agree on the
+    exact-order entry point instead of waiting on each other."""
+    rng = np.random.default_rng(3 if kind == "hybrid" else 4)
+    if kind == "hybrid":
+        lens = [int(v) for v in rng.integers(5, 80, 300)]
+        lens.insert(100, 700)
+        lens.append(700)
+    else:
+        lens = [int(v) for v in rng.integers(20, 60, 60)] + [800, 800]
+    qid = np.concatenate([np.full(l, i) for i, l in enumerate(lens)]).astype(np.int64)
+    n = len(qid)
+    X = rng.integers(-3, 4, size=(n, 5)).astype(np.float32)
+    y = (rng.integers(0, 5, n) * (rng.random(n) < 0.5)).astype(np.float64)
+    return X, y, qid
+
+
+def train_long_lists(fr, X, y, qid):
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    req = fr.TrainRequest.coordinate_ascent()
+    req.measure = "ndcg@10"
+    req.params.num_restarts, req.params.seed, req.params.quiet = 2, 3, True
+    req.params.init_random = False
+    model = ds.train_model(req)
+    return model.to_dict()["Linear"]["weights"], ds.evaluate_mean(model, "ndcg@10")
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -72,9 +102,15 @@ def main():
     model = ds.train_model(req)
     weights = model.to_dict()["Linear"]["weights"]
     mean = ds.evaluate_mean(model, "ndcg@10")
+    long_lists = {}
+    for kind in ("hybrid", "mixed"):
+        X2, y2, q2 = long_list_data(kind)
+        rows2 = frdist.shard_rows(q2, rank, world)
+        long_lists[kind] = train_long_lists(fr, np.ascontiguousarray(X2[rows2]), np.ascontiguousarray(y2[rows2]),
+                                            np.ascontiguousarray(q2[rows2]))
     gathered = [None] * world
     dist.all_gather_object(gathered, (fast.tolist(), exact.tolist(), lin.tolist(), nq_global, weights, mean,
-                                      many.tolist()))
+                                      many.tolist(), long_lists))
     if rank == 0:
         with open(out_path, "w") as fp:
             json.dump({"world": world, "ranks": gathered}, fp)

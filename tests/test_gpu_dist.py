@@ -26,7 +26,7 @@ def test_two_ranks_match_one_gpu(tmp_path):
     import fastrank_b200 as fr
     from fastrank_b200._native import lib
     from fastrank_b200.kernels import DevDataset, dense_query_index
-    from tests.dist_gpu_worker import many_rows, workload
+    from tests.dist_gpu_worker import long_list_data, many_rows, train_long_lists, workload
 
     if lib.fr_dev_device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -57,7 +57,11 @@ def test_two_ranks_match_one_gpu(tmp_path):
     req.params.seed = 7
     req.params.quiet = True
     model = ds.train_model(req)
-    for r_fast, r_exact, r_lin, nq_global, weights, mean, r_many in got["ranks"]:
+    long_lists = {kind: train_long_lists(fr, *long_list_data(kind)) for kind in ("hybrid", "mixed")}
+    for r_fast, r_exact, r_lin, nq_global, weights, mean, r_many, r_long in got["ranks"]:
+        for kind in ("hybrid", "mixed"):   # lists too long for a sweep tile, evenly and unevenly sharded
+            assert r_long[kind][0] == long_lists[kind][0], kind
+            assert r_long[kind][1] == long_lists[kind][1], kind
         assert r_many == many.tolist()
         assert nq_global == nq
         assert r_exact == exact.tolist()   # fixed-point sums do not depend on the sharding
