@@ -262,3 +262,40 @@ def test_long_lists_through_the_api(oracle):
     w = model.to_dict()["Linear"]["weights"]
     exp = oracle.mean(oracle.evaluate_scores(ods, oracle.score_linear(X, w), "ndcg@10"))
     assert ds.evaluate_mean(model, "ndcg@10") == pytest.approx(exp, abs=1e-12)
+
+
+@pytest.mark.parametrize("d,ncand", [(600, 8), (600, 26), (171, 26), (1100, 3), (5, 1), (9, 8)])
+def test_wide_matrices_stage_their_weights_in_chunks(oracle, d, ncand):
+    """The full-rescore kernel keeps up to 32 KB of candidate weights in shared memory: 600
+    features x 8 candidates, 171 x 26 or 1100 x 4 do not fit at once and are staged chunk by
+    chunk (barriers inside the tile loop); feature counts that are not a multiple of the 8-value
+    register block take the remainder path.  Scores stay the reference's left-to-right sums."""
+    rng = np.random.default_rng(d * 31 + ncand)
+    n, q = 1500, 40
+    qid = np.sort(rng.integers(0, q, n)).astype(np.int64)
+    X = rng.normal(size=(n, d)).astype(np.float32)
+    X[:, min(2, d - 1)] = rng.integers(0, 3, n)
+    y = rng.integers(0, 5, n).astype(np.float64)
+    ods = oracle_dataset(oracle, X, y, qid)
+    qidx, nq = dense_qidx(qid)
+    dev = DevDataset(X, y.astype(np.float32), qidx, nq)
+    W = rng.normal(size=(ncand, d))
+    try:
+        plan = dev.plan(0, 10)
+        sums, pq = plan.eval_linear(W)
+        for c in range(ncand):
+            exp = oracle.evaluate_scores(ods, oracle.score_linear(X, W[c]), "ndcg@10")
+            assert np.array_equal(pq[c], exp), (d, c)
+            assert int(sums[c]) == fx_sum(exp)
+        # the exact-order sweep over the same matrix: first, middle and last feature
+        base = rng.normal(size=(3, d))
+        fids = [0, d // 2, d - 1]
+        cands = [[0.0, 0.5, float(base[r, fids[r]])] for r in range(3)]
+        got = plan.coord_sweeps(base, fids, cands)
+        for r in range(3):
+            for k, wv in enumerate(cands[r]):
+                w = base[r].copy()
+                w[fids[r]] = wv
+                assert int(got[r, k]) == fx_sum(oracle.evaluate_scores(ods, oracle.score_linear(X, w), "ndcg@10"))
+    finally:
+        dev.close()
