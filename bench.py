@@ -312,6 +312,28 @@ def run_ours(args, rank, world, local_rank):
     n_kern, kern_ms = dev.profile_read(reset=True)
     dev.profile(False)
     launches = int(lib.fr_dev_kernel_launches()) - launches0
+    # side measurement, outside the timed region and reported next to the roofline: SURVEY 8(d)'s
+    # first row, the full rescore (evaluate_mean for C arbitrary weight vectors per pass over X)
+    full_rescore = []
+    if world == 1:
+        rng = np.random.default_rng(11)
+        peak_gbs = measured_peak_gbs()[0]
+        for c in (1, 8):
+            W = rng.normal(size=(c, d))
+            plan.eval_linear(W, per_query=False)
+            dev.profile(True)
+            dev.profile_read(reset=True)
+            for _ in range(10):
+                plan.eval_linear(W, per_query=False)
+            n_l, l_ms = dev.profile_read(reset=True)
+            dev.profile(False)
+            algo = n_local * d * 4 + n_local * 4 + (nq_local + 1) * 4 + c * d * 8 + c * 8
+            gbs = algo / (l_ms / max(n_l, 1) / 1e3) / 1e9
+            full_rescore.append({"kernel": "linear_batch_kernel<%d,%d>" % (max(c, 2), plan_layout[0]),
+                                 "weight_vectors_per_pass": c, "avg_launch_ms": l_ms / max(n_l, 1),
+                                 "evals_per_s": c / (l_ms / max(n_l, 1) / 1e3),
+                                 "algorithmic_bytes_per_launch": algo, "achieved": gbs, "unit": "GB/s",
+                                 "frac": gbs / peak_gbs})
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -411,6 +433,8 @@ def run_ours(args, rank, world, local_rank):
                        "tile_documents": plan_layout[0], "untiled_queries": plan_layout[1]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }
+        if full_rescore:
+            line["roofline_full_rescore"] = full_rescore
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), file=JSON_OUT, flush=True)
