@@ -298,6 +298,7 @@ struct FastView {
 // Queries longer than the largest tile (long_queries.cu).
 struct LongPlan {
     uint32_t n_long = 0, n_docs = 0;
+    uint32_t chunk = 1;  // candidates per pass over the untiled lists
     DevBuf<uint32_t> lq_off, ld_pos, lq_view, out_idx;
     DevBuf<double> lq_norm, scores, slots, w;
 };

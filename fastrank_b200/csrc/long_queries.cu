@@ -16,7 +16,7 @@ namespace {
 
 constexpr double kFxLong = 1099511627776.0;
 static_assert(FR_FX_BITS == 40, "kFxLong must match FR_FX_BITS");
-constexpr int kLongChunk = 64;  // candidates per pass (bounds the scratch arrays)
+constexpr int kLongChunk = 64;  // most candidates per pass; fewer when the scratch arrays would pass 1 GiB
 constexpr int kLongSmem = 4096;  // list length whose scores are staged in shared memory
 
 struct LongView {
@@ -227,9 +227,11 @@ int build_long_plan(fr_dev_plan *pl, const std::vector<std::vector<uint32_t>> &q
     CU(lp.ld_pos.upload(ld_pos, s));
     CU(lp.lq_view.upload(lq_view, s));
     CU(lp.lq_norm.upload(lq_norm, s));
-    CU(lp.scores.alloc((size_t)kLongChunk * lp.n_docs));
-    CU(lp.slots.alloc((size_t)kLongChunk * lp.n_docs));
-    CU(lp.out_idx.alloc(kLongChunk));
+    // two f64 scratch arrays of chunk x n_docs: 64 candidates per pass unless that passes 1 GiB
+    lp.chunk = (uint32_t)std::max<size_t>(4, std::min<size_t>(kLongChunk, ((size_t)1 << 30) / (16 * (size_t)lp.n_docs)));
+    CU(lp.scores.alloc((size_t)lp.chunk * lp.n_docs));
+    CU(lp.slots.alloc((size_t)lp.chunk * lp.n_docs));
+    CU(lp.out_idx.alloc(lp.chunk));
     CU(lp.w.alloc(1));
     CU(cudaStreamSynchronize(s));
     return 0;
@@ -243,9 +245,9 @@ int eval_long_linear(fr_dev_plan *pl, const double *w_host, size_t wlen, size_t 
     if (lp.n_long == 0 || n_vec == 0) return 0;
     fr_dev_dataset *ds = pl->ds;
     const uint32_t dm = (uint32_t)std::min<size_t>(wlen, ds->d);
-    CU(lp.w.ensure((size_t)kLongChunk * std::max<size_t>(wlen, 1)));
-    for (size_t c0 = 0; c0 < n_vec; c0 += kLongChunk) {
-        const uint32_t nc = (uint32_t)std::min<size_t>(kLongChunk, n_vec - c0);
+    CU(lp.w.ensure((size_t)lp.chunk * std::max<size_t>(wlen, 1)));
+    for (size_t c0 = 0; c0 < n_vec; c0 += lp.chunk) {
+        const uint32_t nc = (uint32_t)std::min<size_t>(lp.chunk, n_vec - c0);
         CU(cudaMemcpyAsync(lp.w.p, w_host + c0 * wlen, sizeof(double) * nc * wlen, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(lp.out_idx.p, out_index + c0, sizeof(uint32_t) * nc, cudaMemcpyHostToDevice, s));
         long_linear_scores_kernel<<<dim3((lp.n_docs + 127) / 128, (nc + kLongKB - 1) / kLongKB), 128, 0, s>>>(
