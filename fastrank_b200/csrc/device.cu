@@ -365,27 +365,22 @@ __global__ void __launch_bounds__(TB) linear_batch_kernel(PlanView P, BatchArgs 
                 __syncthreads();
             }
             if (active) {
-                // XB feature values per document are requested before the previous XB are
-                // consumed, so every warp keeps XB 128-byte row segments in flight
+                // three register blocks of XB feature values rotate: while one is consumed the
+                // loads of the next two are in flight (2 * XB 128-byte row segments per warp)
                 const float *__restrict__ xj = xp + (size_t)j0 * P.ld;
-                float xn[XB];
-                if (n >= (uint32_t)XB) {
+                const uint32_t nb = n / XB;  // full blocks
+                float xa[XB], xb[XB], xc3[XB];
+                auto load = [&](float (&buf)[XB], uint32_t blk) {
+                    if (blk < nb) {
 #pragma unroll
-                    for (int u = 0; u < XB; ++u) xn[u] = ld_x(xj + (size_t)u * P.ld);
-                }
-                uint32_t j = 0;
-                for (; j + XB <= n; j += XB) {
-                    float xc[XB];
-#pragma unroll
-                    for (int u = 0; u < XB; ++u) xc[u] = xn[u];
-                    if (j + 2 * XB <= n) {
-#pragma unroll
-                        for (int u = 0; u < XB; ++u) xn[u] = ld_x(xj + (size_t)(j + XB + u) * P.ld);
+                        for (int u = 0; u < XB; ++u) buf[u] = ld_x(xj + (size_t)(blk * XB + u) * P.ld);
                     }
+                };
+                auto consume = [&](const float (&buf)[XB], uint32_t blk) {
 #pragma unroll
                     for (int u = 0; u < XB; ++u) {
-                        const double xv = (double)xc[u];
-                        const double *wj = s_w + (size_t)(j + u) * KC;
+                        const double xv = (double)buf[u];
+                        const double *wj = s_w + (size_t)(blk * XB + u) * KC;
 #pragma unroll
                         for (int k = 0; k < KC; k += 2) {
                             const double2 w2 = *reinterpret_cast<const double2 *>(wj + k);
@@ -393,7 +388,22 @@ __global__ void __launch_bounds__(TB) linear_batch_kernel(PlanView P, BatchArgs 
                             tk[k + 1] = __dadd_rn(tk[k + 1], __dmul_rn(xv, w2.y));
                         }
                     }
+                };
+                load(xa, 0);
+                load(xb, 1);
+                for (uint32_t blk = 0; blk < nb; blk += 3) {
+                    load(xc3, blk + 2);
+                    consume(xa, blk);
+                    if (blk + 1 < nb) {
+                        load(xa, blk + 3);
+                        consume(xb, blk + 1);
+                    }
+                    if (blk + 2 < nb) {
+                        load(xb, blk + 4);
+                        consume(xc3, blk + 2);
+                    }
                 }
+                const uint32_t j = nb * XB;
                 if (j < n) {
                     float xc[XB];
 #pragma unroll
