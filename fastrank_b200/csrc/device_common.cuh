@@ -84,6 +84,7 @@ struct PinnedBuf {
 
 constexpr int kMaxTile = 1024;  // largest tile of the exact-order kernels
 constexpr int kFastTile = 512;  // largest tile of the batched sweep (sweep_fast.cu)
+constexpr int kMaxSweeps = 8;   // sweeps sharing one pass over X in the batched sweep (one blockIdx.y group)
 #ifdef __CUDACC__
 // cnt += (sj > my) || (sj == my && before): the document at j outranks mine
 // (evaluators.rs:33-49: score descending; on equal scores the earlier local position wins,
@@ -360,6 +361,12 @@ int build_long_plan(fr_dev_plan *pl, const std::vector<std::vector<uint32_t>> &q
 int eval_long_linear(fr_dev_plan *pl, const double *w_host, size_t wlen, size_t n_vec,
                      const uint32_t *out_index, long long *sums_dev, double *perq_dev, int *err_dev,
                      cudaStream_t s);
+// the batched sweep's staged tables (device pointers, see FastArgs in sweep_fast.cu): n_rows
+// candidate rows, row r adds into sums[row_out[r]]
+int eval_long_sweep(fr_dev_plan *pl, const double *base_wt, const uint32_t *fid, uint32_t n_sweeps,
+                    const double *row_w, const uint32_t *row_meta, const uint32_t *row_out,
+                    const uint32_t *grp_row_off, uint32_t n_groups, uint32_t n_rows, uint32_t dm, uint32_t dm8,
+                    long long *sums_dev, double *perq_dev, int *err_dev, cudaStream_t s);
 int eval_long_scores(fr_dev_plan *pl, const double *scores_pos, long long *sums_dev, double *perq_dev,
                      int *err_dev, cudaStream_t s);
 // defined in trees.cu

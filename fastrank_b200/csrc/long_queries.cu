@@ -16,8 +16,9 @@ namespace {
 
 constexpr double kFxLong = 1099511627776.0;
 static_assert(FR_FX_BITS == 40, "kFxLong must match FR_FX_BITS");
-constexpr int kLongChunk = 64;  // most candidates per pass; fewer when the scratch arrays would pass 1 GiB
+constexpr int kLongChunk = 512;  // most candidates per pass; fewer when the scratch arrays would pass 1 GiB
 constexpr int kLongSmem = 4096;  // list length whose scores are staged in shared memory
+constexpr int kSelDepth = 64;    // NDCG cut-offs up to this take the pivot selection
 
 struct LongView {
     const uint32_t *lq_off;   // n_long + 1, into ld_pos
@@ -64,6 +65,63 @@ __global__ void long_linear_scores_kernel(const float *__restrict__ x, size_t ld
         if (k0 + k < nc) scores[(size_t)(k0 + k) * L.n_docs + d] = acc[k];
 }
 
+// The batched sweep's scores for documents of untiled lists, from the tables the tile kernel
+// uses: T_s = sum_j x_j * w_sj (j ascending, separate multiply and add, the swept coordinate
+// zeroed by the host), score(row) = T_s + x_f * row_w -- the arithmetic of sweep_fast_kernel's
+// phase 1 and score_group, so tiled and untiled lists of one call follow the same contract.
+__global__ void long_sweep_scores_kernel(const float *__restrict__ x, size_t ld, uint32_t dm, uint32_t dm8,
+                                         LongView L, const double *__restrict__ base_wt,
+                                         const uint32_t *__restrict__ fid, uint32_t n_sweeps,
+                                         const double *__restrict__ row_w, const uint32_t *__restrict__ row_meta,
+                                         const uint32_t *__restrict__ grp_row_off, uint32_t r_lo, uint32_t r_hi,
+                                         double *__restrict__ scores) {
+    constexpr int NS = kMaxSweeps;
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t g = blockIdx.y;
+    const uint32_t rb = max(grp_row_off[g], r_lo), re = min(grp_row_off[g + 1], r_hi);
+    if (d >= L.n_docs || rb >= re) return;
+    const float *__restrict__ xp = x + L.ld_pos[d];
+    const double *__restrict__ wt = base_wt + (size_t)g * dm8 * NS;
+    double acc[NS];
+    float xf[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        acc[s] = 0.0;
+        const uint32_t sw = g * NS + s;
+        const uint32_t f = sw < n_sweeps ? fid[sw] : 0xffffffffu;
+        xf[s] = f < dm ? __ldg(xp + (size_t)f * ld) : 0.f;
+    }
+    for (uint32_t j0 = 0; j0 < dm; j0 += 8) {
+        float xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xv[u] = j0 + u < dm ? __ldg(xp + (size_t)(j0 + u) * ld) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {  // the table is zero-padded to dm8 coordinates
+            const double xd = (double)xv[u];
+            const double2 *wj = reinterpret_cast<const double2 *>(wt + (size_t)(j0 + u) * NS);
+#pragma unroll
+            for (int s = 0; s < NS; s += 2) {
+                const double2 w2 = __ldg(wj + s / 2);
+                acc[s] = __dadd_rn(acc[s], __dmul_rn(xd, w2.x));
+                acc[s + 1] = __dadd_rn(acc[s + 1], __dmul_rn(xd, w2.y));
+            }
+        }
+    }
+    for (uint32_t r = rb; r < re; ++r) {
+        const uint32_t s = row_meta[r];
+        double ss = acc[0];
+        float xs = xf[0];
+#pragma unroll
+        for (int u = 1; u < NS; ++u) {
+            if (s == (uint32_t)u) {
+                ss = acc[u];
+                xs = xf[u];
+            }
+        }
+        scores[(size_t)(r - r_lo) * L.n_docs + d] = __dadd_rn(ss, __dmul_rn((double)xs, __ldg(row_w + r)));
+    }
+}
+
 __global__ void long_gather_scores_kernel(LongView L, const double *__restrict__ scores_pos,
                                           double *__restrict__ scores) {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,9 +147,77 @@ __global__ void __launch_bounds__(256) long_rank_kernel(PlanView P, LongView L, 
     }
     __syncthreads();
     const double *__restrict__ src = staged ? s_sc : sc;
-    // only documents that can contribute are ranked (local order is gain-ascending, so they are
-    // the tail of the list and whole warps agree)
-    for (uint32_t t = threadIdx.x; t < len; t += blockDim.x) {
+    // NDCG@k on a list much longer than k: only the k best documents matter.  A pivot taken from
+    // a 32-document sample splits the list; if c >= k documents score above it, every document
+    // at or below it has rank >= c >= k and adds nothing, and the documents that outrank a
+    // survivor are survivors themselves -- so ranking the c survivors among themselves gives
+    // their exact ranks (c is a few dozen, not the list length).
+    bool ranked = false;
+    if (staged && P.metric == FR_METRIC_NDCG && (unsigned)P.depth <= (unsigned)kSelDepth &&
+        len >= 8u * (unsigned)P.depth && len >= 64u) {
+        __shared__ double s_smp[32], s_piv[32];
+        __shared__ unsigned s_above[32], s_ncand;
+        __shared__ uint16_t s_cand[kLongSmem];
+        const unsigned depth = (unsigned)P.depth;
+        const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        if (warp == 0) {  // the sample, sorted descending by counting
+            const double v = s_sc[(size_t)lane * len / 32];
+            s_smp[lane] = v;
+            s_piv[lane] = v;  // (defined even if NaNs make ranks collide; that run reports an error)
+            s_above[lane] = 0;
+            __syncwarp();
+            unsigned r = 0;
+            for (unsigned i = 0; i < 32; ++i) {
+                const double o = s_smp[i];
+                r += (o > v) || (o == v && i < lane);
+            }
+            __syncwarp();
+            s_piv[r] = v;
+        }
+        __syncthreads();
+        double pivot = 0.0;
+        bool have = false;
+        for (unsigned i = 0; i < 32 && !have; ++i) {  // pivots from the top until k documents lie above
+            const double p = s_piv[i];
+            unsigned local = 0;
+            for (uint32_t t = threadIdx.x; t < len; t += blockDim.x) local += s_sc[t] > p ? 1u : 0u;
+            local = __reduce_add_sync(0xffffffffu, local);
+            if (lane == 0 && local) atomicAdd(&s_above[i], local);
+            __syncthreads();
+            if (s_above[i] >= depth) {
+                pivot = p;
+                have = true;
+            }
+        }
+        if (have) {
+            if (warp == 0) {  // survivors in list order (the tie-break needs it)
+                unsigned n = 0;
+                for (uint32_t t0 = 0; t0 < len; t0 += 32) {
+                    const uint32_t t = t0 + lane;
+                    const bool in = t < len && s_sc[t] > pivot;
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (in) s_cand[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
+                    n += __popc(m);
+                }
+                if (lane == 0) s_ncand = n;
+            }
+            __syncthreads();
+            const unsigned nc = s_ncand;
+            for (unsigned u = threadIdx.x; u < nc; u += blockDim.x) {
+                const unsigned d = s_cand[u];
+                const double ge = P.gexp[L.ld_pos[base + d]];
+                if (ge == 0.0) continue;
+                const double st = s_sc[d];
+                unsigned cnt = 0;
+                for (unsigned v = 0; v < nc; ++v) count_outranks(cnt, s_sc[s_cand[v]], st, v < u ? 1u : 0u);
+                if (cnt < depth) sl[cnt] = ge / P.lg2[cnt];  // evaluators.rs:265-270
+            }
+            ranked = true;
+        }
+    }
+    // otherwise: every document that can contribute is ranked against the whole list (local order
+    // is gain-ascending, so they are the tail of the list and whole warps agree)
+    for (uint32_t t = threadIdx.x; t < len && !ranked; t += blockDim.x) {
         const uint32_t pos = L.ld_pos[base + t];
         double ge = 0.0;
         bool contrib;
@@ -227,7 +353,7 @@ int build_long_plan(fr_dev_plan *pl, const std::vector<std::vector<uint32_t>> &q
     CU(lp.ld_pos.upload(ld_pos, s));
     CU(lp.lq_view.upload(lq_view, s));
     CU(lp.lq_norm.upload(lq_norm, s));
-    // two f64 scratch arrays of chunk x n_docs: 64 candidates per pass unless that passes 1 GiB
+    // two f64 scratch arrays of chunk x n_docs: 512 candidates per pass unless that passes 1 GiB
     lp.chunk = (uint32_t)std::max<size_t>(4, std::min<size_t>(kLongChunk, ((size_t)1 << 30) / (16 * (size_t)lp.n_docs)));
     CU(lp.scores.alloc((size_t)lp.chunk * lp.n_docs));
     CU(lp.slots.alloc((size_t)lp.chunk * lp.n_docs));
@@ -255,6 +381,25 @@ int eval_long_linear(fr_dev_plan *pl, const double *w_host, size_t wlen, size_t 
         LAUNCHED();
         CU(cudaGetLastError());
         if (rank_chunk(pl, nc, lp.out_idx.p, sums_dev, perq_dev, err_dev, s)) return 1;
+    }
+    return 0;
+}
+
+int eval_long_sweep(fr_dev_plan *pl, const double *base_wt, const uint32_t *fid, uint32_t n_sweeps,
+                    const double *row_w, const uint32_t *row_meta, const uint32_t *row_out,
+                    const uint32_t *grp_row_off, uint32_t n_groups, uint32_t n_rows, uint32_t dm, uint32_t dm8,
+                    long long *sums_dev, double *perq_dev, int *err_dev, cudaStream_t s) {
+    LongPlan &lp = pl->lng;
+    if (lp.n_long == 0 || n_rows == 0) return 0;
+    fr_dev_dataset *ds = pl->ds;
+    for (uint32_t r0 = 0; r0 < n_rows; r0 += lp.chunk) {
+        const uint32_t r1 = std::min(n_rows, r0 + lp.chunk);
+        long_sweep_scores_kernel<<<dim3((lp.n_docs + 127) / 128, n_groups), 128, 0, s>>>(
+            ds->x.p, ds->ld, dm, dm8, long_view(pl), base_wt, fid, n_sweeps, row_w, row_meta, grp_row_off, r0, r1,
+            lp.scores.p);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        if (rank_chunk(pl, r1 - r0, row_out + r0, sums_dev, perq_dev, err_dev, s)) return 1;
     }
     return 0;
 }

@@ -39,7 +39,6 @@
 
 namespace {
 
-constexpr int kMaxSweeps = 8;  // sweeps sharing one pass over X (one blockIdx.y group)
 constexpr int kMaxRows = kMaxSweeps * 64;  // 8 sweeps x (1 + 2 x 25) candidates fit one pass
 constexpr int kSmemTbl = 64;   // discount-table entries kept in shared memory
 constexpr double kFx = 1099511627776.0;
@@ -730,24 +729,6 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
     CU(cudaMemsetAsync(fp.out_dev.p, 0, out_bytes, s));
     if (out_per_query)
         CU(cudaMemsetAsync(pl->perq_dev.p, 0, sizeof(double) * total * (size_t)pl->nq_view, s));
-    if (pl->lng.n_long > 0) {
-        // lists that do not fit a tile: every candidate as a full weight vector, scored and ranked
-        // from HBM (long_queries.cu).  Their sums land in sums_dev BEFORE the tile kernel runs, so
-        // the fused cross-GPU reduction in its tail covers them as well.
-        std::vector<double> full;
-        std::vector<uint32_t> out_index;
-        for (size_t r = 0; r < n_sweeps; ++r) {
-            for (uint32_t k = 0; k < n_cand[r]; ++k) {
-                full.insert(full.end(), base_w + r * wlen, base_w + (r + 1) * wlen);
-                if (fid[r] < wlen) full[full.size() - wlen + fid[r]] = cand_w[r * cand_stride + k];
-                out_index.push_back((uint32_t)(r * cand_stride + k));
-            }
-        }
-        if (eval_long_linear(pl, full.data(), wlen, out_index.size(), out_index.data(), sums_dev,
-                             out_per_query ? pl->perq_dev.p : nullptr, err_dev, s))
-            return 1;
-        CU(cudaStreamSynchronize(s));  // `full` is staged from pageable memory
-    }
     bool first_pass = true;
     for (;;) {
         if (!first_pass) CU(cudaStreamSynchronize(s));  // the staging blob is about to be rewritten
@@ -812,6 +793,13 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         a.mail_world = comm ? (uint32_t)comm->world : 1u;
         a.mail_epoch = fuse_now ? ++comm->mail.epoch : 0u;
         a.mail_words = (uint32_t)total;
+        // lists that do not fit a tile are scored from the same staged tables and ranked from HBM
+        // (long_queries.cu); their sums land in sums_dev BEFORE the tile kernel runs, so the fused
+        // cross-GPU reduction in its tail covers them as well
+        if (pl->lng.n_long > 0 &&
+            eval_long_sweep(pl, a.base_wt, a.fid, (uint32_t)n_sweeps, a.row_w, a.row_meta, a.row_out, a.grp_row_off,
+                            n_groups, (uint32_t)nrows, (uint32_t)dm, (uint32_t)dm8, sums_dev, a.perq, err_dev, s))
+            return 1;
         if (pl->nt == 0 && !fuse_now) continue;
         // the weight table is staged in shared memory while that costs no resident CTA
         bool ws = SmemLayout(128, 1, ((a.dm + 7) & ~7u) * kMaxSweeps).total <= 56 * 1024;
