@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(TB) linear_batch_kernel(PlanView P, BatchArgs 
                 // loads of the next two are in flight (2 * XB 128-byte row segments per warp)
                 const float *__restrict__ xj = xp + (size_t)j0 * P.ld;
                 const uint32_t nb = n / XB;  // full blocks
-                float xa[XB], xb[XB], xc3[XB];
+                float xa[XB], xb[XB], xc[XB];
                 auto load = [&](float (&buf)[XB], uint32_t blk) {
                     if (blk < nb) {
 #pragma unroll
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(TB) linear_batch_kernel(PlanView P, BatchArgs 
                 load(xa, 0);
                 load(xb, 1);
                 for (uint32_t blk = 0; blk < nb; blk += 3) {
-                    load(xc3, blk + 2);
+                    load(xc, blk + 2);
                     consume(xa, blk);
                     if (blk + 1 < nb) {
                         load(xa, blk + 3);
@@ -400,19 +400,19 @@ __global__ void __launch_bounds__(TB) linear_batch_kernel(PlanView P, BatchArgs 
                     }
                     if (blk + 2 < nb) {
                         load(xb, blk + 4);
-                        consume(xc3, blk + 2);
+                        consume(xc, blk + 2);
                     }
                 }
                 const uint32_t j = nb * XB;
                 if (j < n) {
-                    float xc[XB];
+                    float xt[XB];
 #pragma unroll
                     for (int u = 0; u < XB; ++u)
-                        xc[u] = j + u < n ? ld_x(xj + (size_t)(j + u) * P.ld) : 0.0f;
+                        xt[u] = j + u < n ? ld_x(xj + (size_t)(j + u) * P.ld) : 0.0f;
 #pragma unroll
                     for (int u = 0; u < XB; ++u) {
                         if (j + u < n) {
-                            const double xv = (double)xc[u];
+                            const double xv = (double)xt[u];
                             const double *wj = s_w + (size_t)(j + u) * KC;
 #pragma unroll
                             for (int k = 0; k < KC; k += 2) {
