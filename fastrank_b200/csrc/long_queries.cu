@@ -355,6 +355,10 @@ int build_long_plan(fr_dev_plan *pl, const std::vector<std::vector<uint32_t>> &q
     CU(lp.lq_norm.upload(lq_norm, s));
     // two f64 scratch arrays of chunk x n_docs: 512 candidates per pass unless that passes 1 GiB
     lp.chunk = (uint32_t)std::max<size_t>(4, std::min<size_t>(kLongChunk, ((size_t)1 << 30) / (16 * (size_t)lp.n_docs)));
+    if (const char *env = getenv("FASTRANK_LONG_CHUNK")) {  // test knob: candidates per pass
+        const int v = atoi(env);
+        if (v >= 1 && v <= kLongChunk) lp.chunk = (uint32_t)v;
+    }
     CU(lp.scores.alloc((size_t)lp.chunk * lp.n_docs));
     CU(lp.slots.alloc((size_t)lp.chunk * lp.n_docs));
     CU(lp.out_idx.alloc(lp.chunk));

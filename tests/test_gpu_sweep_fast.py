@@ -348,3 +348,36 @@ def test_tile_cap_knob_and_training_with_untiled_lists(oracle, monkeypatch):
     res = oracle.coordinate_ascent(ods, "ndcg@5", num_restarts=2, seed=5)
     assert got["32"][1] == res["n_evals"]
     assert np.allclose(got["32"][0], res["weights"], rtol=0, atol=1e-12)
+
+
+def test_untiled_lists_in_several_scratch_passes(oracle, monkeypatch):
+    """The scratch arrays of the untiled lists hold a bounded number of candidates
+    (FASTRANK_LONG_CHUNK forces 5): both entry points walk the candidate rows in several passes,
+    across sweep-group boundaries, and still return what one pass returns."""
+    rng = np.random.default_rng(84)
+    lens = [int(v) for v in rng.integers(1, 100, 120)] + [700]
+    X, y, qid = _ragged(rng, lens, integer=True)
+    base = rng.integers(-4, 5, size=(10, 6)).astype(np.float64) / 8.0   # 10 sweeps = two sweep groups
+    fids = [int(v) for v in rng.integers(0, 6, 10)]
+    cands = [[float(v) / 4.0 for v in rng.integers(-8, 9, int(rng.integers(1, 9)))] for _ in range(10)]
+    got = {}
+    for chunk in (None, "5"):
+        if chunk is None:
+            monkeypatch.delenv("FASTRANK_LONG_CHUNK", raising=False)
+        else:
+            monkeypatch.setenv("FASTRANK_LONG_CHUNK", chunk)
+        _, _, _, ods, dev = _mk(oracle, 0, 0, 0, 0, X=X, y=y, qid=qid)
+        try:
+            plan = dev.plan(0, 10)
+            assert dev.lib.fr_dev_plan_untiled_queries(plan.ptr) == 1
+            assert dev.lib.fr_dev_plan_has_fast_sweep(plan.ptr) == 1
+            fast, pq = plan.coord_sweeps(base, fids, cands, fast=True, per_query=True)
+            exact = plan.coord_sweeps(base, fids, cands)
+            assert np.array_equal(fast, exact)
+            got[chunk] = (fast.copy(), pq.copy())
+            if chunk is not None:
+                _check(oracle, ods, X, plan, "ndcg@10", base, fids, cands, exact=True)
+        finally:
+            dev.close()
+    assert np.array_equal(got[None][0], got["5"][0])
+    assert np.array_equal(got[None][1], got["5"][1])
