@@ -34,9 +34,11 @@ Rand64::Rand64(unsigned __int128 seed) : state_(0), inc_((kPcgDefaultIncrement <
 uint64_t Rand64::rand_u64() {
     const u128 old = state_;
     state_ = old * kPcgMultiplier + inc_;
+    // oorandom 11.1.0 (the version Cargo.toml:18-19 pins): xorshift the 128-bit state by 29,
+    // keep bits 58..121, rotate right by the top six bits.
     const unsigned rot = (unsigned)(old >> 122);
-    const uint64_t xsl = (uint64_t)(old >> 64) ^ (uint64_t)old;
-    return (xsl >> rot) | (xsl << ((64 - rot) & 63));
+    const uint64_t xsh = (uint64_t)(((old >> 29) ^ old) >> 58);
+    return (xsh >> rot) | (xsh << ((64 - rot) & 63));
 }
 
 double Rand64::rand_float() {
@@ -55,7 +57,9 @@ uint64_t Rand64::rand_range(uint64_t start, uint64_t end) {
             low = (uint64_t)m;
         }
     }
-    return (uint64_t)(m >> 64) + start;
+    // 11.1.0's Rand64 returns the draw over [0, end-start) without adding `start`; every seeded
+    // model of the reference (and its goldens, random_forest.rs:462) depends on that.
+    return (uint64_t)(m >> 64);
 }
 
 // ---------------------------------------------------------------------------------------

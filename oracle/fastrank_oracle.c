@@ -12,11 +12,16 @@
  *   - six single-feature NDCG@5 values   (reference tests/test_with_example_data.py:16-23)
  *   - tie-order known answer [4,3,1,2,5] (reference src/evaluators.rs:61-79)
  *   - compute_dcg known answer 0.7328    (reference src/evaluators.rs:285-295)
- * UNPINNED for the random-number stream: the reference draws from the crate
- * `oorandom` pinned `=11.1.0` (reference Cargo.toml:18-19) which is not vendored under
- * /root/reference and cannot be fetched offline.  fro_rng_* restates its published
- * algorithm (PCG XSL-RR 128/64) from memory; coordinate-ascent trajectories therefore
- * match the reference only up to the RNG stream (no reference test pins them).
+ * PINNED for the random-number stream as well: the reference draws from the crate
+ * `oorandom` pinned `=11.1.0` (reference Cargo.toml:18-19), which is not vendored under
+ * /root/reference.  fro_rng_* restates that version's published algorithm -- including its
+ * two quirks: the 128 -> 64 bit output function is `rotr64((u64)(((s >> 29) ^ s) >> 58), s >> 122)`
+ * (not PCG's XSL-RR), and Rand64::rand_range() forgets to add range.start -- and is anchored
+ * on artefacts the reference itself produced with it (tests/test_oracle_golden.py):
+ *   - random-forest determinism golden 0.4367914517387043 (reference src/random_forest.rs:427-463,
+ *     tests/test_with_example_data.py:175-201): RNG + sampling + induction + scoring + NDCG@5
+ *   - the coordinate-ascent weights and NDCG@5 printed by examples/FastRankDemo.ipynb
+ *     (cells 4-6, seed 1234567): RNG + reset + shuffle + the whole line-search driver
  *
  * The reference (Rust) cannot be compiled in this image (no cargo/rustc), so there is
  * no oracle/_ref build; every function below cites the reference lines it follows.
@@ -34,9 +39,12 @@
 #define FRO_RR 2
 
 /* ------------------------------------------------------------------------------------
- * RNG: oorandom::Rand64 (PCG XSL-RR 128/64), restated from the crate's published
- * algorithm.  Call sites in the reference: coordinate_ascent.rs:27,53,199,212;
- * randutil.rs:8,24; random_forest.rs:143,293,306.
+ * RNG: oorandom::Rand64 as of the pinned crate version 11.1.0 (reference Cargo.toml:18-19),
+ * restated from the crate's published algorithm.  Call sites in the reference:
+ * coordinate_ascent.rs:27,53,199,212; randutil.rs:8,24; random_forest.rs:143,293,306;
+ * evaluators.rs:161-165.  Known answers: seed 42 -> 12410087264455502793, 359948335059059064,
+ * 14020691344464510033; Rand64::new(0xdeadbeef).rand_u64() = 8208548815909702348 (the default
+ * seed of both learners, coordinate_ascent.rs:27-34).
  * ---------------------------------------------------------------------------------- */
 typedef unsigned __int128 u128;
 typedef struct {
@@ -55,9 +63,11 @@ static u128 fro_pcg_default_inc(void) {
 uint64_t fro_rng_u64(fro_rng *r) {
     u128 old = r->state;
     r->state = old * fro_pcg_mult() + r->inc;
+    /* 11.1.0's output function: a 128-bit xorshift by 29, bits 58..121 kept, rotated right
+     * by the top six state bits (PCG's 64/32 XSH-RR recipe transplanted to 128/64). */
     uint32_t rot = (uint32_t)(old >> 122);
-    uint64_t xsl = (uint64_t)(old >> 64) ^ (uint64_t)old;
-    return (xsl >> rot) | (xsl << ((64 - rot) & 63));
+    uint64_t xsh = (uint64_t)(((old >> 29) ^ old) >> 58);
+    return (xsh >> rot) | (xsh << ((64 - rot) & 63));
 }
 
 void fro_rng_seed(fro_rng *r, uint64_t seed_lo, uint64_t seed_hi) {
@@ -69,22 +79,24 @@ void fro_rng_seed(fro_rng *r, uint64_t seed_lo, uint64_t seed_hi) {
     (void)fro_rng_u64(r);
 }
 
-/* raw state injection, used by the test that cross-checks the step/output function
- * against numpy.random.PCG64 (same generator family, different seeding). */
+/* raw state injection, used by the test that cross-checks the 128-bit LCG step against
+ * numpy.random.PCG64 (same multiplier and increment convention, different output function). */
 void fro_rng_set_raw(fro_rng *r, uint64_t st_lo, uint64_t st_hi, uint64_t inc_lo, uint64_t inc_hi) {
     r->state = (((u128)st_hi) << 64) | st_lo;
     r->inc = (((u128)inc_hi) << 64) | inc_lo;
 }
 
 double fro_rng_float(fro_rng *r) {
-    /* oorandom keeps MANTISSA_DIGITS+1 = 54 high bits and scales by 2^-54 (as recalled;
-     * unpinned, see header). */
+    /* oorandom keeps MANTISSA_DIGITS+1 = 54 high bits and scales by 2^-54. */
     uint64_t u = fro_rng_u64(r) >> 10;
     return (double)u * (1.0 / 18014398509481984.0);
 }
 
 uint64_t fro_rng_range(fro_rng *r, uint64_t start, uint64_t end) {
-    /* Lemire's nearly-divisionless bounded draw over [0, end-start), shifted by start. */
+    /* Lemire's nearly-divisionless bounded draw over [0, end-start).  Version 11.1.0 returns
+     * it WITHOUT adding range.start (Rand32 adds it, Rand64 does not) -- the reason the crate
+     * is pinned "to prevent seeds from changing" (Cargo.toml:18) -- so shuffle's
+     * rand_range(i..n) (randutil.rs:24) yields [0, n-i).  The goldens bake this in. */
     uint64_t s = end - start;
     u128 m = (u128)fro_rng_u64(r) * (u128)s;
     uint64_t leftover = (uint64_t)m;
@@ -95,7 +107,7 @@ uint64_t fro_rng_range(fro_rng *r, uint64_t start, uint64_t end) {
             leftover = (uint64_t)m;
         }
     }
-    return (uint64_t)(m >> 64) + start;
+    return (uint64_t)(m >> 64);
 }
 
 /* randutil.rs:21-27 */

@@ -114,7 +114,12 @@ class OracleDataset:
     """Dense view: X f32[N,D] row-major, gains f32[N], qid strings, per-query id lists."""
 
     def __init__(self, X: np.ndarray, gains: np.ndarray, qids: Sequence[str],
-                 docids: Optional[List[Optional[str]]] = None):
+                 docids: Optional[List[Optional[str]]] = None,
+                 present: Optional[np.ndarray] = None):
+        # present[i, f]: instance i carries feature f (instance.rs:61-77: a Dense32 row knows
+        # ids below its own length, a Sparse32 row the listed ones).  None = DenseDataset,
+        # where nothing is missing (dense_dataset.rs:139-147).
+        self.present = present
         self.X = np.ascontiguousarray(X, dtype=np.float32)
         self.gains = np.ascontiguousarray(gains, dtype=np.float32)
         self.qids = [str(q) for q in qids]
@@ -183,10 +188,19 @@ def load_libsvm(path: str) -> OracleDataset:
             docids.append(comment)
             rows.append(feats)
     X = np.zeros((len(rows), max_fid + 1), dtype=np.float32)
+    present = np.zeros((len(rows), max_fid + 1), dtype=bool)
     for i, feats in enumerate(rows):
         for k, v in feats.items():
             X[i, k] = v
-    return OracleDataset(X, np.asarray(labels, dtype=np.float32), qids, docids)
+        # instance.rs:104-122: dense when at least half of 1..max own id is listed, and then
+        # the row is max_own_id + 1 long (ids below that read 0.0, ids beyond are None)
+        own_max = max(feats) if feats else 1
+        density = len(feats) / own_max if own_max > 0 else float("inf")
+        if density >= 0.5:
+            present[i, : own_max + 1] = True
+        else:
+            present[i, list(feats)] = True
+    return OracleDataset(X, np.asarray(labels, dtype=np.float32), qids, docids, present)
 
 
 def load_qrel(path: str) -> Dict[str, Dict[str, float]]:
@@ -338,7 +352,7 @@ def coordinate_ascent(ds: OracleDataset, measure: str, *, num_restarts=5, num_ma
 
 
 class Rng:
-    """oorandom::Rand64 restatement (unpinned; see the C header)."""
+    """oorandom::Rand64 (=11.1.0) restatement; pinned by the goldens listed in the C header."""
 
     def __init__(self, seed: int = 0):
         self._buf = C.create_string_buffer(lib().fro_sizeof_rng() + 16)

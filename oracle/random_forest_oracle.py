@@ -3,8 +3,9 @@
 Follows /root/reference/src/random_forest.rs line by line, including the sort-by-feature the
 product's host trainer (fastrank_b200/csrc/random_forest.cpp) replaces with counting passes, so
 that the two can be compared tree for tree.  numpy for the sorts, plain Python loops for the
-sequential f64 sums (small cases only).  RNG: oracle.Rng (oorandom restated; unpinned, see
-fastrank_oracle.c) -- the same generator the product uses, so same seed => same samples.
+sequential f64 sums (small cases only).  RNG: oracle.Rng (oorandom =11.1.0 restated, see
+fastrank_oracle.c).  Pinned end to end by the reference's determinism golden
+(random_forest.rs:427-463 -> 0.4367914517387043; tests/test_oracle_golden.py).
 
 Where the reference leaves an order unspecified (sort_unstable among equal keys, HashMap
 iteration) this file makes the same deterministic choice as the product: stable sorts, the last
@@ -144,7 +145,7 @@ def _split_candidate(params, fid, X, gains, instances, fstats):  # :211-286
     return {"fid": fid, "split": position, "importance": imp, "lhs": ids[:right], "rhs": ids[right:]}
 
 
-def _learn_recursive(params, X, gains, features, instances, depth, trace=None, path=""):  # :362-408
+def _learn_recursive(params, X, gains, features, instances, depth, trace=None, path="", present=None):  # :362-408
     if not features or not instances:
         return None
     if depth >= params["max_depth"]:
@@ -153,9 +154,10 @@ def _learn_recursive(params, X, gains, features, instances, depth, trace=None, p
         return None
     best = None
     for fid in features:
-        st = _Stats()  # FeatureStats::compute, normalizers.rs:13-36 (dense data: nothing is missing)
+        st = _Stats()  # FeatureStats::compute, normalizers.rs:13-36: missing values are skipped
         for i in instances:
-            st.push(float(X[i, fid]))
+            if present is None or present[i, fid]:
+                st.push(float(X[i, fid]))
         if not st.finished():
             continue
         cand = _split_candidate(params, fid, X, gains, instances, st)
@@ -167,10 +169,10 @@ def _learn_recursive(params, X, gains, features, instances, depth, trace=None, p
             best = cand
     if best is None:
         return None
-    lhs = _learn_recursive(params, X, gains, features, best["lhs"], depth + 1, trace, path + "L")
+    lhs = _learn_recursive(params, X, gains, features, best["lhs"], depth + 1, trace, path + "L", present)
     if lhs is None:
         lhs = {"LeafNode": _compute_output(best["lhs"], gains)}
-    rhs = _learn_recursive(params, X, gains, features, best["rhs"], depth + 1, trace, path + "R")
+    rhs = _learn_recursive(params, X, gains, features, best["rhs"], depth + 1, trace, path + "R", present)
     if rhs is None:
         rhs = {"LeafNode": _compute_output(best["rhs"], gains)}
     return {"FeatureSplit": {"fid": int(best["fid"]), "split": float(best["split"]), "lhs": lhs, "rhs": rhs}}
@@ -198,7 +200,7 @@ def learn_forest(ds: "orc.OracleDataset", params: Dict, traces: Optional[List[Di
             if q in qsel:
                 instances.extend(int(i) for i in ds.by_query[q])
         trace = {} if traces is not None else None
-        root = _learn_recursive(params, X, gains, fsel, instances, 1, trace)
+        root = _learn_recursive(params, X, gains, fsel, instances, 1, trace, "", ds.present)
         if traces is not None:
             traces.append(trace)
         if root is None:

@@ -38,3 +38,13 @@ def oracle():
 @pytest.fixture(scope="session")
 def trec_train(oracle):
     return oracle.load_libsvm(os.path.join(GOLDEN, "trec_news_2018.train"))
+
+
+@pytest.fixture(scope="session")
+def trec_test(oracle):
+    return oracle.load_libsvm(os.path.join(GOLDEN, "trec_news_2018.test"))
+
+
+# the reference's own test module is a fixture that tests/test_gpu_reference_suite.py runs in a
+# subprocess (needs `import fastrank` -> compat/, cwd with examples/): not collected here
+collect_ignore_glob = ["golden/ref_tests/*"]

@@ -143,27 +143,85 @@ def test_regression_tree_known_answer(oracle, goldens):
     assert oracle.score_model(X, {"DecisionTree": tree}).tolist() == [float(y) for y in g["ys"]]
 
 
-def test_pcg_step_matches_numpy_pcg64(oracle):
-    # The generator family (PCG XSL-RR 128/64, default multiplier) is cross-checked against
-    # numpy's PCG64 by injecting the same raw state; the seeding/range details of oorandom
-    # 11.1.0 remain unpinned (see the oracle header).
+def test_oorandom_known_answers(oracle, goldens):
+    # oorandom =11.1.0 (Cargo.toml:18-19): first draws for seed 42 and the learners' default seed
+    # Rand64::new(0xdeadbeef).rand_u64() (coordinate_ascent.rs:27-34, random_forest.rs:143-146)
+    g = goldens["oorandom_known_answers"]
+    rng = oracle.Rng(42)
+    assert [rng.u64() for _ in range(3)] == g["seed_42_first_three_u64"]
+    assert oracle.Rng(0xDEADBEEF).u64() == g["default_seed"]
+
+
+def test_lcg_step_matches_numpy_pcg64(oracle):
+    # The 128-bit LCG underneath (multiplier, increment convention) is the one numpy's PCG64
+    # uses; only the output function differs (oorandom: rotr64(((s >> 29) ^ s) >> 58, s >> 122)).
     bg = np.random.PCG64(1234)
     st = bg.state["state"]
+    state, inc = st["state"], st["inc"]
     rng = oracle.Rng(0)
-    rng.set_raw(st["state"], st["inc"])
-    ours = [rng.u64() for _ in range(16)]
-    # numpy steps the state BEFORE producing output; one draw re-aligns the streams
-    theirs = [int(x) for x in bg.random_raw(17)]
-    assert ours[1:] == theirs[:15] or ours == theirs[:16] or ours[:15] == theirs[1:16]
+    rng.set_raw(state, inc)
+    mult = 47026247687942121848144207491837523525
+    mask128, mask64 = (1 << 128) - 1, (1 << 64) - 1
+    for _ in range(16):
+        x = (((state >> 29) ^ state) >> 58) & mask64
+        rot = state >> 122
+        expect = ((x >> rot) | (x << ((64 - rot) & 63))) & mask64
+        assert rng.u64() == expect
+        state = (state * mult + inc) & mask128
+    # ... and numpy's next raw draw comes from the same successor state (XSL-RR of it)
+    nxt = (st["state"] * mult + inc) & mask128
+    xsl = ((nxt >> 64) ^ nxt) & mask64
+    r = nxt >> 122
+    assert int(bg.random_raw(1)[0]) == ((xsl >> r) | (xsl << ((64 - r) & 63))) & mask64
 
 
-def test_rng_range_and_float_bounds(oracle):
+def test_rng_range_drops_the_range_start(oracle):
+    # 11.1.0's Rand64::rand_range returns a draw over [0, end - start): the start is not added
+    # (randutil.rs:24 therefore shuffles with rand_range(i..n) in [0, n - i)).
     rng = oracle.Rng(42)
-    for _ in range(200):
+    seen = set()
+    for _ in range(400):
         v = rng.range(3, 10)
-        assert 3 <= v < 10
+        assert 0 <= v < 7
+        seen.add(v)
         f = rng.float()
-        assert 0.0 <= f <= 1.0
+        assert 0.0 <= f < 1.0
+    assert seen == set(range(7))
+
+
+def test_random_forest_determinism_golden(oracle, trec_train, goldens):
+    # random_forest.rs:427-463 / tests/test_with_example_data.py:175-201: 10 trees, seed 42 ->
+    # NDCG@5 0.4367914517387043.  Pins RNG stream + sampling + induction (FeatureStats skip rows
+    # that do not carry the feature, normalizers.rs:21-27) + ensemble scoring + NDCG.
+    from oracle import random_forest_oracle as rfo
+
+    g = goldens["rf_determinism_ndcg5"]
+    assert trec_train.present is not None and not trec_train.present.all()
+    model = rfo.learn_forest(trec_train, g["params"])
+    got = oracle.mean(oracle.evaluate_scores(trec_train, oracle.score_model(trec_train.X, model), "ndcg@5"))
+    assert abs(got - g["expected"]) < g["tolerance"], got
+
+
+def test_notebook_coordinate_ascent_golden(oracle, trec_train, trec_test, goldens):
+    # examples/FastRankDemo.ipynb cells 4-5: the reference's own output for seed 1234567 with the
+    # default parameters -- pins reset / shuffle / the whole line-search driver end to end.
+    g = goldens["notebook_coordinate_ascent"]
+    res = oracle.coordinate_ascent(trec_train, g["request"]["measure"], seed=g["request"]["seed"])
+    assert np.allclose(res["weights"], g["weights"], rtol=0, atol=g["weights_tolerance"])
+    test_ndcg = oracle.mean(oracle.evaluate_scores(trec_test, oracle.score_linear(trec_test.X, res["weights"]), "ndcg@5"))
+    assert "%.3g" % test_ndcg == g["test_ndcg5_printed"]
+
+
+def test_notebook_random_forest_golden(oracle, trec_train, trec_test, goldens):
+    # examples/FastRankDemo.ipynb cells 3, 5: 100 trees, both sampling rates 0.5, seed 1234567
+    from oracle import random_forest_oracle as rfo
+
+    g = goldens["notebook_random_forest"]
+    params = {"min_leaf_support": 10, "max_depth": 8, "split_candidates": 3, "split_method": "SquaredError"}
+    params.update(g["params"])
+    model = rfo.learn_forest(trec_train, params)
+    test_ndcg = oracle.mean(oracle.evaluate_scores(trec_test, oracle.score_model(trec_test.X, model), "ndcg@5"))
+    assert "%.3g" % test_ndcg == g["test_ndcg5_printed"]
 
 
 def test_ca_improves_and_is_deterministic(oracle, trec_train):
