@@ -280,6 +280,13 @@ struct FastPlan {
     DevBuf<uint2> tasks;             // .x = qs | qe << 16, .y = t0 | n << 16 (tile-local documents)
     DevBuf<uint8_t> pd_cls;          // plan doc -> gain class
     DevBuf<double> disc_tbl;         // [n_cls][tbl_r]  (2^gain - 1) / log2(r + 2)
+    // NDCG@k with k <= 16 and <= 15 gain classes: sweep_packed_kernel (sweep_packed.cuh)
+    bool packed_ok = false;
+    DevBuf<uint32_t> pk_q_task_off;     // nq_plan + 1
+    DevBuf<uint32_t> pk_tile_task_off;  // nt + 1
+    DevBuf<uint32_t> pk_tasks;          // t0 | n << 16, chunks of <= 16 documents, grouped by query
+    DevBuf<uint16_t> pk_q_order;        // tile-local query indices, costliest first
+    DevBuf<double> pk_tbl;              // [n_cls + 1][tbl_r], row 0 zeros
     // per-call work buffers (sweep_fast.cu documents the layout): one input blob = transposed
     // weights + the call's candidates flattened into rows, one output blob = sums, error flags,
     // tile counters; each moves with a single copy through pinned memory

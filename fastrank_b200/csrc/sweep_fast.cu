@@ -95,6 +95,56 @@ __device__ __forceinline__ float ld_stream(const float *p) {
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
+// misc words
+enum { M_F = 0, M_TILE = 16, M_NEXT = 17, M_CTR = 18, M_SWROW = 20 /* 9 entries */ };
+
+// ---- fused all-reduce over peer memory ----
+// Tail of both sweep kernels.  The last CTA of this GPU to flush its sums stores the GPU's
+// partial sums into every rank's mailbox (NVLink peer stores), raises its arrival flag there,
+// waits for the flags of all ranks in its own mailbox and leaves the rank-ordered integer total
+// in A.sums: the kernel that ranks is the kernel that reduces, no separate collective launch
+// follows.
+template <int TB>
+__device__ __forceinline__ void fused_allreduce_tail(const FastArgs &A, int *s_misc) {
+    const int t = threadIdx.x;
+    __threadfence();
+    __syncthreads();
+    if (t == 0) s_misc[M_TILE] = atomicAdd(A.done_ctr, 1u) == gridDim.x * gridDim.y - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_misc[M_TILE]) return;
+    __threadfence();
+    const uint32_t world = A.mail_world, me = A.mail_rank, buf = A.mail_epoch & 1u, nw = A.mail_words;
+    const size_t slot = sizeof(long long) * kMailWords;
+    for (uint32_t r = 0; r < world; ++r) {
+        long long *dst = (long long *)(A.mail_peers[r] + ((size_t)buf * world + me) * slot);
+        for (uint32_t i = t; i < nw; i += TB) dst[i] = __ldcg(A.sums + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((uint32_t)t < world) {
+        unsigned *flag = (unsigned *)(A.mail_peers[t] + Mailbox::flags_offset((int)world)) + buf * world + me;
+        st_release_sys(flag, A.mail_epoch);
+        const unsigned *mine = (const unsigned *)(A.mail_peers[me] + Mailbox::flags_offset((int)world)) + buf * world + t;
+        const long long t_begin = clock64();
+        while (ld_acquire_sys(mine) != A.mail_epoch) {
+            if (clock64() - t_begin > 8000000000ll) {  // ~4 s: a peer never made this call
+                atomicOr(A.err, ERR_PEER_TIMEOUT);
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    const unsigned char *box = A.mail_peers[me] + (size_t)buf * world * slot;
+    for (uint32_t i = t; i < nw; i += TB) {
+        long long total = 0;
+        for (uint32_t r = 0; r < world; ++r)
+            total += *(const volatile long long *)(box + (size_t)r * slot + sizeof(long long) * i);
+        A.sums[i] = total;
+    }
+}
+
 template <int TB>
 struct SlotType {
     typedef uint8_t type;  // document ids 1..128 / gain classes 1..255
@@ -127,8 +177,6 @@ struct SmemLayout {
     }
 };
 
-// misc words
-enum { M_F = 0, M_TILE = 16, M_NEXT = 17, M_CTR = 18, M_SWROW = 20 /* 9 entries */ };
 
 // One warp task: rank W documents [t0, t0 + n) of the query occupying tile-local [qs, qe)
 // under the 32 candidate rows of the lanes (myrow = this lane's row of the score matrix).
@@ -470,48 +518,7 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     for (int idx = t; idx < R; idx += TB)
         atomicAdd((unsigned long long *)(A.sums + A.row_out[row0 + idx]), s_sum[idx]);
     if (A.mail_peers == nullptr) return;
-
-    // ---- fused all-reduce over peer memory ----
-    // The last CTA of this GPU to flush its sums stores the GPU's partial sums into every rank's
-    // mailbox (NVLink peer stores), raises its arrival flag there, waits for the flags of all
-    // ranks in its own mailbox and leaves the rank-ordered integer total in A.sums: the kernel
-    // that ranks is the kernel that reduces, no separate collective launch follows.
-    __threadfence();
-    __syncthreads();
-    if (t == 0) s_misc[M_TILE] = atomicAdd(A.done_ctr, 1u) == gridDim.x * gridDim.y - 1 ? 1 : 0;
-    __syncthreads();
-    if (!s_misc[M_TILE]) return;
-    __threadfence();
-    const uint32_t world = A.mail_world, me = A.mail_rank, buf = A.mail_epoch & 1u, nw = A.mail_words;
-    const size_t slot = sizeof(long long) * kMailWords;
-    for (uint32_t r = 0; r < world; ++r) {
-        long long *dst = (long long *)(A.mail_peers[r] + ((size_t)buf * world + me) * slot);
-        for (uint32_t i = t; i < nw; i += TB) dst[i] = __ldcg(A.sums + i);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((uint32_t)t < world) {
-        unsigned *flag = (unsigned *)(A.mail_peers[t] + Mailbox::flags_offset((int)world)) + buf * world + me;
-        st_release_sys(flag, A.mail_epoch);
-        const unsigned *mine = (const unsigned *)(A.mail_peers[me] + Mailbox::flags_offset((int)world)) + buf * world + t;
-        const long long t_begin = clock64();
-        while (ld_acquire_sys(mine) != A.mail_epoch) {
-            if (clock64() - t_begin > 8000000000ll) {  // ~4 s: a peer never made this call
-                atomicOr(A.err, ERR_PEER_TIMEOUT);
-                break;
-            }
-            __nanosleep(200);
-        }
-    }
-    __syncthreads();
-    __threadfence_system();
-    const unsigned char *box = A.mail_peers[me] + (size_t)buf * world * slot;
-    for (uint32_t i = t; i < nw; i += TB) {
-        long long total = 0;
-        for (uint32_t r = 0; r < world; ++r)
-            total += *(const volatile long long *)(box + (size_t)r * slot + sizeof(long long) * i);
-        A.sums[i] = total;
-    }
+    fused_allreduce_tail<TB>(A, s_misc);
 }
 
 template <int TB, int TD, bool WS>
@@ -558,6 +565,54 @@ int launch_fast(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStrea
     auto *ev = pl->ds->prof_slot();
     if (ev) cudaEventRecord(ev->first, stream);
     kernel<<<dim3(gx, n_groups), TB, L.total, stream>>>(pv, fv, args);
+    if (ev) cudaEventRecord(ev->second, stream);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+#include "sweep_packed.cuh"
+
+template <int TB, bool WS>
+int launch_packed(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStream_t stream) {
+    const uint32_t dm8 = (a.dm + 7) & ~7u;
+    const PackedLayout L(TB, WS ? dm8 * kMaxSweeps : 0u);
+    auto kernel = sweep_packed_kernel<TB, WS>;
+    static std::mutex mu;
+    static std::map<std::pair<int, size_t>, int> cache;
+    int occ = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        const auto key = std::make_pair(pl->ds->device, L.total);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            int optin = 0;
+            CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, pl->ds->device));
+            CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TB, L.total));
+            it = cache.emplace(key, occ).first;
+        }
+        occ = it->second;
+    }
+    if (occ < 1) return fail("sweep_packed_kernel does not fit on an SM");
+    uint64_t total = (uint64_t)pl->sm_count * (uint64_t)occ;
+    uint32_t gx = (uint32_t)std::max<uint64_t>(1, total / n_groups);
+    if (gx > pl->nt) gx = std::max<uint32_t>(pl->nt, 1);  // an empty shard still takes part in the reduction
+    PlanView pv = pl->view();
+    FastArgs args = a;
+    args.n_split = gx / 4u;
+    PackedView v;
+    v.q_task_off = pl->fast.pk_q_task_off.p;
+    v.q_order = pl->fast.pk_q_order.p;
+    v.tile_task_off = pl->fast.pk_tile_task_off.p;
+    v.tasks = pl->fast.pk_tasks.p;
+    v.pd_cls = pl->fast.pd_cls.p;
+    v.tbl = pl->fast.pk_tbl.p;
+    v.tbl_r = pl->fast.tbl_r;
+    v.n_cls = pl->fast.n_cls;
+    auto *ev = pl->ds->prof_slot();
+    if (ev) cudaEventRecord(ev->first, stream);
+    kernel<<<dim3(gx, n_groups), TB, L.total, stream>>>(pv, v, args);
     if (ev) cudaEventRecord(ev->second, stream);
     LAUNCHED();
     CU(cudaGetLastError());
@@ -667,6 +722,58 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
     CU(fp.tile_task_off.upload(tile_task_off, s));
     CU(fp.tasks.upload(tasks, s));
     fp.ok = true;
+    // sweep_packed_kernel: NDCG@k, k <= 16 ranks of 4 bits in one register per candidate
+    fp.packed_ok = false;
+    if (ndcg && fp.n_cls >= 1 && fp.n_cls <= 15 && pl->depth <= 16) {
+        std::vector<uint32_t> q_task_off{0}, pk_tile_off{0}, pk_tasks;
+        std::vector<uint16_t> q_order(pq_local.size(), 0);
+        std::vector<std::pair<uint64_t, uint16_t>> cost;
+        for (uint32_t tile = 0; tile + 1 < tile_q_off.size(); ++tile) {
+            cost.clear();
+            for (uint32_t pq = tile_q_off[tile]; pq < tile_q_off[tile + 1]; ++pq) {
+                const uint32_t start = pq_local[pq] & 0xffffu, len = pq_local[pq] >> 16;
+                uint64_t qcost = 64;  // fold + bookkeeping
+                uint32_t i = 0;
+                while (i < len) {
+                    if (ds->gain_pos[pd_pos[pq_doc0[pq] + i]] == 0.0f) {
+                        ++i;
+                        continue;
+                    }
+                    uint32_t run = 1;  // documents that can contribute: 2^gain - 1 != 0
+                    while (i + run < len && ds->gain_pos[pd_pos[pq_doc0[pq] + i + run]] != 0.0f) ++run;
+                    // chunks of 16 / 8 / 4: a walk of W documents costs len * (3 + 2 W) instructions
+                    while (run > 0) {
+                        const uint32_t n = run >= 13 ? std::min<uint32_t>(run, 16) : (run > 8 ? 8 : run);
+                        const uint32_t w = n > 8 ? 16 : (n > 4 ? 8 : 4);
+                        pk_tasks.push_back((start + i) | (n << 16));
+                        qcost += (uint64_t)len * (3 + 2 * w) + (uint64_t)w * w;
+                        i += n;
+                        run -= n;
+                    }
+                }
+                q_task_off.push_back((uint32_t)pk_tasks.size());
+                cost.emplace_back(qcost, (uint16_t)(pq - tile_q_off[tile]));
+            }
+            std::stable_sort(cost.begin(), cost.end(),
+                             [](const std::pair<uint64_t, uint16_t> &a, const std::pair<uint64_t, uint16_t> &b) {
+                                 return a.first > b.first;
+                             });
+            for (size_t k = 0; k < cost.size(); ++k) q_order[tile_q_off[tile] + k] = cost[k].second;
+            pk_tile_off.push_back((uint32_t)pk_tasks.size());
+        }
+        // table with a leading row of zeros: tag 0 = nothing ranked there
+        std::vector<double> tbl0((size_t)(fp.n_cls + 1) * fp.tbl_r, 0.0);
+        for (size_t c = 0; c < cls_gain.size(); ++c) {
+            const double ge = std::pow(2.0, (double)cls_gain[c]) - 1.0;  // evaluators.rs:268
+            for (uint32_t r = 0; r < fp.tbl_r; ++r) tbl0[(c + 1) * fp.tbl_r + r] = ge / std::log2((double)r + 2.0);
+        }
+        CU(fp.pk_q_task_off.upload(q_task_off, s));
+        CU(fp.pk_tile_task_off.upload(pk_tile_off, s));
+        CU(fp.pk_tasks.upload(pk_tasks, s));
+        CU(fp.pk_q_order.upload(q_order, s));
+        CU(fp.pk_tbl.upload(tbl0, s));
+        fp.packed_ok = true;
+    }
     return 0;
 }
 
@@ -725,6 +832,15 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
     }
     fr_dev_comm *comm = pl->comm && pl->comm->world > 1 ? pl->comm : nullptr;
     const bool fuse = comm && comm->mail.ok && total <= kMailWords;
+    // NDCG@k (k <= 16) takes the register-packed kernel; it tests for NaN scores only where T or
+    // x_f is not finite, so candidates that are not finite themselves go to the general kernel
+    bool use_packed = fp.packed_ok;
+    for (size_t r = 0; r < n_sweeps && use_packed; ++r)
+        for (uint32_t k = 0; k < n_cand[r]; ++k)
+            if (!std::isfinite(cand_w[r * cand_stride + k])) use_packed = false;
+    if (const char *env = getenv("FASTRANK_SWEEP_KERNEL")) {  // test knob: "tile" forces the general kernel
+        if (std::string(env) == "tile") use_packed = false;
+    }
     size_t pass = 0;
     CU(cudaMemsetAsync(fp.out_dev.p, 0, out_bytes, s));
     if (out_per_query)
@@ -805,7 +921,15 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         bool ws = SmemLayout(128, 1, ((a.dm + 7) & ~7u) * kMaxSweeps).total <= 56 * 1024;
         if (const char *env = getenv("FASTRANK_WSMEM")) ws = atoi(env) != 0;
         int rc;
-        if (pl->tb == 128) {
+        if (use_packed) {
+            const bool wsp = PackedLayout(pl->tb, ((a.dm + 7) & ~7u) * kMaxSweeps).total <= (pl->tb == 128 ? 56u : 100u) * 1024;
+            if (pl->tb == 128)
+                rc = wsp ? launch_packed<128, true>(pl, a, n_groups, s) : launch_packed<128, false>(pl, a, n_groups, s);
+            else if (pl->tb == 256)
+                rc = wsp ? launch_packed<256, true>(pl, a, n_groups, s) : launch_packed<256, false>(pl, a, n_groups, s);
+            else
+                rc = wsp ? launch_packed<512, true>(pl, a, n_groups, s) : launch_packed<512, false>(pl, a, n_groups, s);
+        } else if (pl->tb == 128) {
             if (ws)
                 rc = fp.td == 8 ? launch_fast<128, 8, true>(pl, a, n_groups, s)
                                 : launch_fast<128, 4, true>(pl, a, n_groups, s);

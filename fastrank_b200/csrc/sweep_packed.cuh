@@ -1,0 +1,312 @@
+// sweep_packed.cuh -- the batched coordinate-ascent sweep for NDCG@k, k <= 16 (included by
+// sweep_fast.cu, which documents the work being replaced and the arithmetic contract; both
+// kernels produce the same bits).
+//
+// What differs from sweep_fast_kernel (the general kernel: any metric, any cut-off):
+//   * no score matrix and no CTA-wide phases.  Phase 1 (thread = document, one pass over the
+//     tile's slice of X for all sweeps) leaves  T2[s][t] = { T_s(t), x_{f_s}(t) }  in shared memory;
+//     after ONE barrier the tile's work is a queue of independent WARP items
+//     (query, group of 32 candidate rows): lane = candidate row, scores are formed where they are
+//     compared,  score = T + x_f * c_lane  (one LDS.128, one DMUL, one DADD per walked document).
+//   * ranking by counting as before (DSETP + predicated add per comparison; the tie rule is the
+//     tile order), W = 16 / 8 / 4 documents per walk, pairs inside a chunk compared once.
+//   * a candidate's top-k lives in ONE 64-bit register per lane: 4 bits per rank hold the gain
+//     class of the document ranked there (<= 15 classes), so there is no slot buffer to clear,
+//     scatter into or synchronise on; the same warp folds it at once -- the reference's
+//     left-to-right f64 sum of (2^gain - 1) / log2(rank + 2) over ranks 0..k-1
+//     (evaluators.rs:255-272) from the host-built table -- and adds round(value * 2^40) to the
+//     row's sum.
+// Two barriers per tile instead of two per row group, ~0.55x the instructions.
+#pragma once
+
+struct PackedView {
+    const uint32_t *q_task_off;     // [nq_plan + 1] first task of a plan query
+    const uint16_t *q_order;        // [nq_plan] tile-local query indices, costliest first
+    const uint32_t *tile_task_off;  // [nt + 1]
+    const uint32_t *tasks;          // t0 | n << 16 (tile-local documents of one query, n <= 16)
+    const uint8_t *pd_cls;          // plan doc -> gain class
+    const double *tbl;              // [n_cls + 1][tbl_r]: row 0 zeros (empty slot), row c + 1 = class c
+    uint32_t tbl_r, n_cls;
+};
+
+struct PackedLayout {
+    size_t t2, sum, roww, tbl, qd, tasks, order, cls, rowsw, misc, w, total;
+    __host__ __device__ PackedLayout(int tb, uint32_t w_doubles) {
+        size_t o = 0;
+        t2 = o;     o += sizeof(double2) * kMaxSweeps * (size_t)tb;
+        sum = o;    o += sizeof(unsigned long long) * kMaxRows;
+        roww = o;   o += sizeof(double) * kMaxRows;
+        tbl = o;    o += sizeof(double) * 16 * 16;
+        qd = o;     o += sizeof(uint2) * tb;
+        tasks = o;  o += sizeof(uint32_t) * tb;
+        order = o;  o += align16(sizeof(uint16_t) * tb);
+        cls = o;    o += align16(tb);
+        rowsw = o;  o += kMaxRows;
+        misc = o;   o += 256;
+        w = o;      o += sizeof(double) * w_doubles;
+        total = o;
+    }
+};
+
+// documents i < j of one chunk (j later in tile order, so j loses ties): exactly one outranks the other
+__device__ __forceinline__ void count_pair(unsigned &ci, unsigned &cj, double si, double sj) {
+    asm("{ .reg .pred p; setp.gt.f64 p, %2, %3; @p add.u32 %0, %0, 1; @!p add.u32 %1, %1, 1; }"
+        : "+r"(ci), "+r"(cj)
+        : "d"(sj), "d"(si));
+}
+
+// Ranks the W documents [t0, t0 + n) of the query occupying tile-local [qs, qe) under this lane's
+// candidate c and files their gain classes by rank into `packed` (ranks below lim only).
+template <int W>
+__device__ __forceinline__ void rank_chunk(const double2 *__restrict__ trow, double c, int qs, int qe, int t0, int n,
+                                           unsigned lim, const uint8_t *__restrict__ s_cls,
+                                           unsigned long long &packed) {
+    double st[W];
+    unsigned cnt[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const int tt = t0 + i < qe ? t0 + i : qe - 1;
+        const double2 tx = trow[tt];
+        st[i] = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+        cnt[i] = 0;
+    }
+    int jq = qs;
+#pragma unroll 2
+    for (; jq < t0; ++jq) {  // documents that win ties against the chunk's
+        const double2 tx = trow[jq];
+        const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+#pragma unroll
+        for (int i = 0; i < W; ++i) count_ge(cnt[i], sj, st[i]);
+    }
+#pragma unroll
+    for (int j = 1; j < W; ++j) {
+        if (j < n) {
+#pragma unroll
+            for (int i = 0; i < j; ++i) count_pair(cnt[i], cnt[j], st[i], st[j]);
+        }
+    }
+    jq = t0 + n;
+#pragma unroll 2
+    for (; jq < qe; ++jq) {  // documents that lose ties
+        const double2 tx = trow[jq];
+        const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+#pragma unroll
+        for (int i = 0; i < W; ++i) count_gt(cnt[i], sj, st[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        if (i < n && cnt[i] < lim)
+            packed |= (unsigned long long)((unsigned)s_cls[t0 + i] + 1u) << (cnt[i] << 2);
+    }
+}
+
+template <int TB, bool WS>
+__global__ void __launch_bounds__(TB, (TB == 128 ? 4 : (TB == 256 ? 2 : 1)))
+sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NS = kMaxSweeps;
+    const int t = threadIdx.x, lane = t & 31;
+    const uint32_t s0 = blockIdx.y * NS;
+    const int ns = (int)min((uint32_t)NS, A.n_sweeps - s0);
+    const uint32_t dm = A.dm;
+    const uint32_t row0 = A.grp_row_off[blockIdx.y];
+    const int R = (int)(A.grp_row_off[blockIdx.y + 1] - row0);  // rows of this sweep group
+    const int G = (R + 31) >> 5;
+    const uint32_t dm8 = (dm + 7) & ~7u;
+    const PackedLayout L(TB, WS ? dm8 * NS : 0u);
+    double2 *s_t2 = (double2 *)(smem_raw + L.t2);  // [NS][TB]
+    unsigned long long *s_sum = (unsigned long long *)(smem_raw + L.sum);
+    double *s_roww = (double *)(smem_raw + L.roww);
+    double *s_tbl = (double *)(smem_raw + L.tbl);
+    uint2 *s_qd = (uint2 *)(smem_raw + L.qd);
+    uint32_t *s_tasks = (uint32_t *)(smem_raw + L.tasks);
+    uint16_t *s_order = (uint16_t *)(smem_raw + L.order);
+    uint8_t *s_cls = (uint8_t *)(smem_raw + L.cls);
+    uint8_t *s_rowsw = (uint8_t *)(smem_raw + L.rowsw);
+    int *s_misc = (int *)(smem_raw + L.misc);
+    const double *__restrict__ wg = A.base_wt + (size_t)blockIdx.y * dm8 * NS;
+    double *s_w = (double *)(smem_raw + L.w);
+    const uint32_t tbl_r = V.tbl_r;
+
+    // ---- per-launch setup ----
+    for (int idx = t; idx < kMaxRows; idx += TB) {
+        s_rowsw[idx] = idx < R ? (uint8_t)A.row_meta[row0 + idx] : (uint8_t)0;
+        s_roww[idx] = idx < R ? A.row_w[row0 + idx] : 0.0;
+        s_sum[idx] = 0ull;
+    }
+    for (uint32_t idx = t; idx < (V.n_cls + 1) * tbl_r; idx += TB) s_tbl[idx] = V.tbl[idx];
+    if (WS)
+        for (uint32_t idx = t; idx < dm8 * NS; idx += TB) s_w[idx] = wg[idx];
+    __syncthreads();
+    if (t < NS) {
+        // a sweep without rows in this pass is not computed
+        bool has_rows = false;
+        for (int r = 0; r < R; ++r) has_rows |= (int)s_rowsw[r] == t;
+        s_misc[M_F + t] = (t < ns && has_rows) ? (int)A.fid[s0 + t] : -1;
+    }
+    if (t == 0) s_misc[M_TILE] = (int)atomicAdd(A.tile_ctr + blockIdx.y, 1u);
+    __syncthreads();
+    uint32_t fs[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) fs[s] = (uint32_t)s_misc[M_F + s];
+    int nan_seen = 0;
+
+    // Work items: whole tiles first; the last n_split tiles are handed out as quarter items (a
+    // quarter of the row groups each, phase 1 repeated) so that the SMs drain together.
+    const uint32_t n_split = G >= 4 ? min(P.nt, A.n_split) : 0u;
+    const uint32_t n_whole = P.nt - n_split;
+    const uint32_t n_items = G > 0 ? n_whole + 4u * n_split : 0u;
+    uint32_t next_item = n_items;
+    for (uint32_t item = G > 0 ? (uint32_t)s_misc[M_TILE] : n_items; item < n_items; item = next_item) {
+        if (t == 0) s_misc[M_NEXT] = (int)atomicAdd(A.tile_ctr + blockIdx.y, 1u);
+        uint32_t tile = item;
+        int g_begin = 0, g_end = G;
+        if (item >= n_whole) {
+            const uint32_t j = item - n_whole, part = j & 3u;
+            tile = n_whole + (j >> 2);
+            g_begin = (int)((uint32_t)G * part / 4u);
+            g_end = (int)((uint32_t)G * (part + 1u) / 4u);
+        }
+        const uint32_t doc0 = P.tile_doc_off[tile];
+        const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
+        const bool active = t < nd;
+        const uint32_t pos = active ? P.pd_pos[doc0 + t] : 0u;
+        const uint32_t task0 = V.tile_task_off[tile];
+        const int ntask = (int)(V.tile_task_off[tile + 1] - task0);
+        const uint32_t q0 = P.tile_q_off[tile];
+        const int nqt = (int)(P.tile_q_off[tile + 1] - q0);
+        if (t < ntask) s_tasks[t] = V.tasks[task0 + t];
+        if (t < nqt) {
+            const uint32_t tb0 = V.q_task_off[q0 + t], tb1 = V.q_task_off[q0 + t + 1];
+            s_qd[t] = make_uint2(P.pq_local[q0 + t], (tb0 - task0) | ((tb1 - tb0) << 16));
+            s_order[t] = V.q_order[q0 + t];
+        }
+        s_cls[t] = active ? __ldg(V.pd_cls + doc0 + t) : (uint8_t)0;
+
+        // ---- phase 1: one pass over the tile's features for every sweep (as sweep_fast_kernel) ----
+        {
+            double acc[NS];
+            float xf[NS];
+            const float *__restrict__ xp = P.x + pos;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                acc[s] = 0.0;
+                xf[s] = fs[s] < dm ? ld_stream(xp + (size_t)fs[s] * P.ld) : 0.f;
+            }
+            float cur[8], nxt[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cur[u] = (uint32_t)u < dm ? ld_stream(xp + (size_t)u * P.ld) : 0.f;
+            for (uint32_t j0 = 0; j0 < dm; j0 += 8) {
+                if (j0 + 16 <= dm) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) nxt[u] = ld_stream(xp + (size_t)(j0 + 8 + u) * P.ld);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        nxt[u] = j0 + 8 + u < dm ? ld_stream(xp + (size_t)(j0 + 8 + u) * P.ld) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double xd = (double)cur[u];
+                    const double2 *__restrict__ wj =
+                        (const double2 *)((WS ? (const double *)s_w : wg) + (size_t)(j0 + u) * NS);
+#pragma unroll
+                    for (int s = 0; s < NS; s += 2) {
+                        const double2 w2 = WS ? wj[s >> 1] : __ldg(wj + (s >> 1));
+                        acc[s] = __dadd_rn(acc[s], __dmul_rn(xd, w2.x));
+                        acc[s + 1] = __dadd_rn(acc[s + 1], __dmul_rn(xd, w2.y));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+            }
+            // A score T + x_f * c can only be NaN (the reference's panic, model.rs:49) when T or x_f
+            // is not finite -- candidates are checked on the host -- so the per-candidate test runs
+            // for such documents only.
+            bool odd = false;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                odd |= !(fabs(acc[s]) <= 1.7976931348623157e308) || !(fabsf(xf[s]) <= 3.402823466e38f);
+                s_t2[(size_t)s * TB + t] = make_double2(active ? acc[s] : 0.0, active ? (double)xf[s] : 0.0);
+            }
+            if (odd && active) {
+                for (int r = (g_begin << 5); r < min(R, g_end << 5); ++r) {
+                    const int s = s_rowsw[r];
+                    double ss = acc[0];
+                    float xs32 = xf[0];
+#pragma unroll
+                    for (int u = 1; u < NS; ++u) {
+                        if (s == u) {
+                            ss = acc[u];
+                            xs32 = xf[u];
+                        }
+                    }
+                    const double sc = __dadd_rn(ss, __dmul_rn((double)xs32, s_roww[r]));
+                    if (sc != sc) nan_seen = 1;
+                }
+            }
+        }
+        if (t == 0) s_misc[M_CTR] = 0;
+        __syncthreads();
+
+        // ---- warp items: (query, row group) ----
+        const int ng = g_end - g_begin;
+        const int nwork = nqt * ng;
+        for (;;) {
+            int idx = 0;
+            if (lane == 0) idx = atomicAdd(&s_misc[M_CTR], 1);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (idx >= nwork) break;
+            const int k = idx / ng;
+            const int g = g_begin + (idx - k * ng);
+            const int ql = s_order[k];
+            const uint2 qd = s_qd[ql];
+            const int qs = (int)(qd.x & 0xffffu), len = (int)(qd.x >> 16), qe = qs + len;
+            const int tk0 = (int)(qd.y & 0xffffu), ntk = (int)(qd.y >> 16);
+            const unsigned lim = (unsigned)P.depth < (unsigned)len ? (unsigned)P.depth : (unsigned)len;
+            const int row = (g << 5) + lane;
+            const bool live = row < R;
+            const int rowc = live ? row : R - 1;
+            const double c = s_roww[rowc];
+            const double2 *trow = s_t2 + (size_t)s_rowsw[rowc] * TB;
+            unsigned long long packed = 0ull;
+            for (int tk = tk0; tk < tk0 + ntk; ++tk) {
+                const uint32_t w = s_tasks[tk];
+                const int t0 = (int)(w & 0xffffu), n = (int)(w >> 16);
+                if (n > 8)
+                    rank_chunk<16>(trow, c, qs, qe, t0, n, lim, s_cls, packed);
+                else if (n > 4)
+                    rank_chunk<8>(trow, c, qs, qe, t0, n, lim, s_cls, packed);
+                else
+                    rank_chunk<4>(trow, c, qs, qe, t0, n, lim, s_cls, packed);
+            }
+            // fold: ranks 0 .. lim-1 in order (evaluators.rs:265-270); an empty slot adds +0.0 like a
+            // zero-gain document does in the reference
+            const uint32_t pq = q0 + ql;
+            const double norm = P.pq_norm[pq];
+            double value = 0.0;
+            if (norm == norm) {  // Some(ideal), evaluators.rs:351-358
+                double dcg = 0.0;
+                for (unsigned r = 0; r < lim; ++r) {
+                    const unsigned tag = (unsigned)(packed >> (r << 2)) & 15u;
+                    dcg = __dadd_rn(dcg, s_tbl[tag * tbl_r + r]);
+                }
+                if (dcg > norm) atomicOr(A.err, ERR_DCG_ABOVE_IDEAL);
+                value = dcg / norm;
+            }
+            if (live) {
+                if (A.perq) A.perq[(size_t)A.row_out[row0 + row] * P.nq_view + P.pq_view[pq]] = value;
+                const long long fx = __double2ll_rn(value * kFx);
+                atomicAdd(&s_sum[row], (unsigned long long)fx);
+            }
+        }
+        next_item = (uint32_t)s_misc[M_NEXT];
+        __syncthreads();  // T2 and the tile tables are rewritten by the next item
+    }
+    if (nan_seen) atomicOr(A.err, ERR_NAN_SCORE);
+    __syncthreads();
+    for (int idx = t; idx < R; idx += TB)
+        atomicAdd((unsigned long long *)(A.sums + A.row_out[row0 + idx]), s_sum[idx]);
+    if (A.mail_peers == nullptr) return;
+    fused_allreduce_tail<TB>(A, s_misc);
+}

@@ -381,3 +381,46 @@ def test_untiled_lists_in_several_scratch_passes(oracle, monkeypatch):
             dev.close()
     assert np.array_equal(got[None][0], got["5"][0])
     assert np.array_equal(got[None][1], got["5"][1])
+
+
+@pytest.mark.parametrize("depth", [1, 5, 10, 16])
+def test_packed_kernel_equals_general_kernel_bit_for_bit(oracle, monkeypatch, depth):
+    """NDCG@k with k <= 16 is served by sweep_packed_kernel (top-k of a candidate in one 64-bit
+    register); FASTRANK_SWEEP_KERNEL=tile forces the general tile kernel.  Same scores, same
+    comparisons, same fold order: sums and per-query values must agree bit for bit on float data
+    (ragged lists up to 512 documents, negative gains, queries without relevant documents, 8 x 51
+    candidates so that row groups straddle sweeps, and a plan with few tiles so that quarter items
+    are handed out)."""
+    rng = np.random.default_rng(90 + depth)
+    lens = [int(v) for v in rng.integers(1, 70, 400)] + [130, 255, 1, 2, 33]
+    if depth == 10:
+        lens += [300, 512]
+    X, y, qid = _ragged(rng, lens, d=20)
+    y[rng.random(len(y)) < 0.05] = -1.0
+    y[qid == 3] = 0.0
+    _, _, _, ods, dev = _mk(oracle, 0, 0, 0, 0, X=X, y=y, qid=qid)
+    base = rng.normal(size=(8, 20))
+    base /= np.abs(base).sum(axis=1, keepdims=True)
+    fids = [int(v) for v in rng.integers(0, 20, 8)]
+    cands = [_line(base[r, fids[r]], 51) for r in range(8)]
+    got = {}
+    try:
+        plan = dev.plan(0, depth)
+        for which in ("tile", None):
+            if which is None:
+                monkeypatch.delenv("FASTRANK_SWEEP_KERNEL", raising=False)
+            else:
+                monkeypatch.setenv("FASTRANK_SWEEP_KERNEL", which)
+            got[which] = plan.coord_sweeps(base, fids, cands, fast=True, per_query=True)
+        assert np.array_equal(got["tile"][0], got[None][0])
+        assert np.array_equal(got["tile"][1], got[None][1])
+        # and against the oracle on a few candidates
+        name = "ndcg@%d" % depth
+        for r, k in ((0, 0), (3, 17), (7, 50)):
+            w = base[r].copy()
+            w[fids[r]] = cands[r][k]
+            exp = oracle.evaluate_scores(ods, oracle.score_linear(X, w), name)
+            assert np.abs(got[None][1][r, k] - exp).max() < 1e-9 or (got[None][1][r, k] != exp).mean() < 0.01
+            assert abs(got[None][1][r, k].mean() - exp.mean()) < 1e-9
+    finally:
+        dev.close()
