@@ -25,7 +25,7 @@ CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-ffp-contract=of
 
 CU_SOURCES = ["device.cu", "sweep_fast.cu", "trees.cu", "long_queries.cu", "rf_induction.cu"]
 CXX_SOURCES = ["dataset.cpp", "model.cpp", "evaluator.cpp", "coordinate_ascent.cpp",
-               "random_forest.cpp", "training.cpp", "capi.cpp"]
+               "random_forest.cpp", "training.cpp", "capi.cpp", "io_helper.cpp"]
 
 
 def _newer(target: str, deps) -> bool:

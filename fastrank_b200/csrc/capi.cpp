@@ -13,6 +13,10 @@
 
 #include <chrono>
 
+#include <atomic>
+
+#include <sstream>
+
 #include "host.hpp"
 
 using namespace frb;
@@ -89,15 +93,23 @@ const CModel &need(const CModel *m) {
     return *m;
 }
 
-std::vector<double> score_all(const Model &model, ParentDataset &parent) {
-    const std::vector<uint64_t> code = model.lower();
+// Scores of every instance of the parent dataset (json_api.rs:59-69), straight into `out`
+// (parent.n doubles).  The dataset's stream and its score scratch are shared device state: the
+// call is serialised with evaluators and trainers on the same dataset (use_mu), so concurrent
+// predict / evaluate / train calls from several threads cannot read each other's scores.
+void score_all_into(const CModel &m, ParentDataset &parent, double *out) {
     fr_dev_dataset *dev = parent.device();
-    fr_dev_model *dm = nullptr;
-    if (fr_dev_model_create(dev, code.data(), code.size(), &dm)) throw Error(fr_dev_last_error());
-    std::vector<double> scores(parent.n);
-    const int rc = fr_dev_score_model(dev, dm, scores.data());
-    fr_dev_model_destroy(dm);
+    std::lock_guard<std::recursive_mutex> lock(parent.use_mu);
+    bool owned = false;
+    fr_dev_model *dm = parent.device_model(m.model, m.uid, &owned);
+    const int rc = fr_dev_score_model(dev, dm, out);
+    if (owned) fr_dev_model_destroy(dm);
     if (rc) throw Error(fr_dev_last_error());
+}
+
+std::vector<double> score_all(const CModel &m, ParentDataset &parent) {
+    std::vector<double> scores(parent.n);
+    score_all_into(m, parent, scores.data());
     return scores;
 }
 
@@ -110,6 +122,11 @@ std::string rust_display_f64(double v) {  // Display for f64: shortest digits, n
 }
 
 }  // namespace
+
+CModel::CModel(frb::Model m) : model(std::move(m)) {
+    static std::atomic<uint64_t> next{1};
+    uid = next.fetch_add(1, std::memory_order_relaxed);
+}
 
 extern "C" {
 
@@ -289,7 +306,7 @@ const CResult *train_model(void *train_request_json_ptr, void *dataset) {
             const CoordinateAscentParams p = CoordinateAscentParams::from_json(params->obj[0].second);
             Evaluator ev(d.view, m, qrel.get());
             const double setup = seconds_since(t_begin);
-            CModel *out = new CModel{coordinate_ascent_learn(p, d.view, ev, &stats)};
+            CModel *out = new CModel(coordinate_ascent_learn(p, d.view, ev, &stats));
             stats.seconds_setup = setup;
             stats.seconds_total = seconds_since(t_begin);
             set_last_train_stats(stats);
@@ -299,7 +316,7 @@ const CResult *train_model(void *train_request_json_ptr, void *dataset) {
             const RandomForestParams p = RandomForestParams::from_json(params->obj[0].second);
             Evaluator ev(d.view, m, qrel.get());
             const double setup = seconds_since(t_begin);
-            CModel *out = new CModel{random_forest_learn(p, d.view, ev, &stats)};
+            CModel *out = new CModel(random_forest_learn(p, d.view, ev, &stats));
             stats.seconds_setup = setup;
             stats.seconds_total = seconds_since(t_begin);
             set_last_train_stats(stats);
@@ -311,7 +328,7 @@ const CResult *train_model(void *train_request_json_ptr, void *dataset) {
 
 const CResult *model_from_json(const void *json_str) {
     return result_call([&]() -> const void * {
-        return new CModel{Model::from_json(parse_json(accept_str("json_str", json_str)))};
+        return new CModel(Model::from_json(parse_json(accept_str("json_str", json_str))));
     });
 }
 
@@ -335,7 +352,7 @@ const void *evaluate_by_query(const CModel *model, const CDataset *dataset, cons
         const Measure measure = Measure::parse(accept_str("evaluator_name", evaluator));
         Evaluator ev(d.view, measure, qrel ? qrel->qrel.get() : nullptr);  // ffi.rs:253-255
         std::vector<double> per_query;
-        ev.evaluate_mean(m.model, &per_query);
+        ev.evaluate_mean(m.model, &per_query, m.uid);
         json::Value out = json::Value::object();
         const auto &qs = ev.view_queries();
         for (size_t k = 0; k < qs.size(); ++k)
@@ -348,7 +365,7 @@ const void *predict_scores(const CModel *model, const CDataset *dataset) {
     return json_call([&]() -> std::string {  // json_api.rs:53-72
         const CModel &m = need(model);
         const CDataset &d = need(dataset);
-        const std::vector<double> scores = score_all(m.model, *d.view.parent);
+        const std::vector<double> scores = score_all(m, *d.view.parent);
         std::string out = "{";
         bool first = true;
         auto emit = [&](uint32_t id) {
@@ -377,12 +394,12 @@ const void *predict_dense_f64(const CModel *model, const CDataset *dataset, doub
         if (!out) throw Error("NULL pointer: out");
         ParentDataset &p = *d.view.parent;
         if (n_out < p.n) throw Error("predict_dense_f64: output buffer smaller than the parent dataset");
-        const std::vector<double> scores = score_all(m.model, p);
         if (d.view.sampled) {
+            const std::vector<double> scores = score_all(m, p);
             for (size_t i = 0; i < n_out; ++i) out[i] = NAN;
             for (uint32_t id : d.view.instances) out[id] = scores[id];
         } else {
-            std::copy(scores.begin(), scores.end(), out);
+            score_all_into(m, p, out);
             for (size_t i = p.n; i < n_out; ++i) out[i] = NAN;
         }
         return nullptr;
@@ -399,7 +416,7 @@ const void *evaluate_mean_f64(const CModel *model, const CDataset *dataset, cons
         if (!out_mean) throw Error("NULL pointer: out_mean");
         const Measure measure = Measure::parse(accept_str("evaluator_name", evaluator));
         Evaluator ev(d.view, measure, qrel ? qrel->qrel.get() : nullptr);
-        *out_mean = ev.evaluate_mean(m.model, nullptr);
+        *out_mean = ev.evaluate_mean(m.model, nullptr, m.uid);
         return nullptr;
     } catch (const std::exception &e) {
         return dup_cstr(error_json(e.what()));
@@ -414,9 +431,8 @@ const void *predict_to_trecrun(const CModel *model, const CDataset *dataset, con
         const std::string path = accept_str("output_path", output_path);
         const std::string system = accept_str("system_name", system_name);
         ParentDataset &p = *d.view.parent;
-        std::ofstream out(path);
-        if (!out) throw Error("could not create " + path);
-        const std::vector<double> scores = score_all(m.model, p);
+        std::ostringstream out;  // written at the end, compressed by extension (io_helper.rs:31-48)
+        const std::vector<double> scores = score_all(m, p);
         size_t written = 0;
         // Export path: scores come from the GPU; ordering the rows of the
         // text file is done here with the reference comparator (evaluators.rs:33-49).
@@ -437,8 +453,8 @@ const void *predict_to_trecrun(const CModel *model, const CDataset *dataset, con
                     << rust_display_f64(scores[id]) << ' ' << system << '\n';
                 ++written;
             }
-            out.flush();
         }
+        write_file_by_extension(path, out.str());
         return std::to_string(written);
     });
 }

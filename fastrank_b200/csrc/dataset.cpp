@@ -111,8 +111,7 @@ static float parse_f32_strict(const std::string &tok, bool *ok) {
 }
 
 std::shared_ptr<QRel> QRel::load_file(const std::string &path) {
-    std::ifstream in(path);
-    if (!in) throw Error("Os { code: 2, kind: NotFound, message: \"No such file or directory\" }: " + path);
+    std::istringstream in(read_file_by_extension(path));  // .gz / .bz2 / .zst by extension (io_helper.rs:18-29)
     auto out = std::make_shared<QRel>();
     std::string line;
     size_t num = 0;
@@ -165,7 +164,34 @@ json::Value QRel::to_json() const {
 // ---------------------------------------------------------------------------------------
 ParentDataset::~ParentDataset() {
     plan_cache.clear();  // plans reference the device dataset
+    for (auto &kv : model_cache) fr_dev_model_destroy(kv.second);
     if (dev) fr_dev_dataset_destroy(dev);
+}
+
+fr_dev_model *ParentDataset::device_model(const Model &m, uint64_t uid, bool *owned) {
+    std::lock_guard<std::recursive_mutex> lock(use_mu);
+    *owned = uid == 0;
+    if (uid != 0) {
+        for (size_t i = 0; i < model_cache.size(); ++i) {
+            if (model_cache[i].first == uid) {
+                auto hit = model_cache[i];
+                model_cache.erase(model_cache.begin() + (long)i);
+                model_cache.push_back(hit);
+                return hit.second;
+            }
+        }
+    }
+    const std::vector<uint64_t> code = m.lower();
+    fr_dev_model *dm = nullptr;
+    if (fr_dev_model_create(device(), code.data(), code.size(), &dm)) throw Error(fr_dev_last_error());
+    if (uid != 0) {
+        if (model_cache.size() >= 4) {
+            fr_dev_model_destroy(model_cache.front().second);
+            model_cache.erase(model_cache.begin());
+        }
+        model_cache.emplace_back(uid, dm);
+    }
+    return dm;
 }
 
 fr_dev_dataset *ParentDataset::device() {
@@ -226,15 +252,7 @@ DatasetView load_ranksvm(const std::string &path, const std::string *feature_nam
             ds->feature_names[(uint32_t)id] = m.second.s;
         }
     }
-    if (path.size() > 3) {
-        for (const char *ext : {".gz", ".bz2", ".zst"}) {
-            const size_t el = strlen(ext);
-            if (path.size() >= el && path.compare(path.size() - el, el, ext) == 0)
-                throw Error(path + ": compressed input is out of scope for this build; decompress first");
-        }
-    }
-    std::ifstream in(path);
-    if (!in) throw Error(path + ": Os { code: 2, kind: NotFound, message: \"No such file or directory\" }");
+    std::istringstream in(read_file_by_extension(path));  // .gz / .bz2 / .zst by extension (io_helper.rs:18-29)
 
     struct Row {
         std::vector<std::pair<uint32_t, float>> feats;

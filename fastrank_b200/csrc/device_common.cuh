@@ -284,7 +284,7 @@ struct FastPlan {
     bool packed_ok = false;
     DevBuf<uint32_t> pk_q_task_off;     // nq_plan + 1
     DevBuf<uint32_t> pk_tile_task_off;  // nt + 1
-    DevBuf<uint32_t> pk_tasks;          // t0 | n << 16, chunks of <= 16 documents, grouped by query
+    DevBuf<uint4> pk_tasks;             // chunks of <= 16 documents, grouped by query (PackedView::tasks)
     DevBuf<uint16_t> pk_q_order;        // tile-local query indices, costliest first
     DevBuf<double> pk_tbl;              // [n_cls + 1][tbl_r], row 0 zeros
     // per-call work buffers (sweep_fast.cu documents the layout): one input blob = transposed

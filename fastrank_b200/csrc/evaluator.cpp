@@ -136,7 +136,7 @@ double Evaluator::mean_from_fx(int64_t fx) const {
     return std::ldexp((double)fx, -FR_FX_BITS) / (double)nq;
 }
 
-double Evaluator::evaluate_mean(const Model &m, std::vector<double> *per_query) const {
+double Evaluator::evaluate_mean(const Model &m, std::vector<double> *per_query, uint64_t model_uid) const {
     int64_t fx = 0;
     if (per_query) per_query->assign(num_queries(), 0.0);
     double *pq = per_query && !per_query->empty() ? per_query->data() : nullptr;
@@ -145,12 +145,10 @@ double Evaluator::evaluate_mean(const Model &m, std::vector<double> *per_query) 
         const double *w = m.weights.empty() ? &zero : m.weights.data();
         if (fr_dev_eval_linear_batch(plan_, w, m.weights.size(), 1, &fx, pq)) throw Error(fr_dev_last_error());
     } else {
-        const std::vector<uint64_t> code = m.lower();
-        fr_dev_model *dm = nullptr;
-        if (fr_dev_model_create(view_.parent->device(), code.data(), code.size(), &dm))
-            throw Error(fr_dev_last_error());
+        bool owned = false;
+        fr_dev_model *dm = view_.parent->device_model(m, model_uid, &owned);
         const int rc = fr_dev_eval_model(plan_, dm, &fx, pq);
-        fr_dev_model_destroy(dm);
+        if (owned) fr_dev_model_destroy(dm);
         if (rc) throw Error(fr_dev_last_error());
     }
     return mean_from_fx(fx);

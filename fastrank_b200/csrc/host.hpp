@@ -138,9 +138,15 @@ struct ParentDataset {
     fr_dev_dataset *dev = nullptr;             // uploaded on first use
     std::recursive_mutex use_mu;               // one evaluator at a time drives the device state
     std::vector<std::shared_ptr<PlanHolder>> plan_cache;  // plans without judgments, newest last
+    // models lowered and uploaded for this dataset's device, keyed by CModel::uid, newest last:
+    // predict / evaluate in a loop with the same model do not lower, upload and lay out a forest
+    // again (500 trees: ~100 ms of host work for a 3 ms kernel).  Guarded by use_mu.
+    std::vector<std::pair<uint64_t, fr_dev_model *>> model_cache;
 
     ~ParentDataset();
     fr_dev_dataset *device();                  // throws Error when no GPU is usable
+    // the device form of `m`; uid 0 = a temporary model, built and handed to the caller (*owned)
+    fr_dev_model *device_model(const Model &m, uint64_t uid, bool *owned);
     std::string feature_name(uint32_t fid) const;
 };
 
@@ -162,6 +168,10 @@ struct DatasetView {
 
 DatasetView load_ranksvm(const std::string &path, const std::string *feature_names_path);
 DatasetView make_dense(size_t n, size_t d, const float *x, const double *y, const int64_t *qids);
+
+// io_helper.rs:18-48: whole files, transparently (de)compressed when the name ends in .gz / .bz2 / .zst
+std::string read_file_by_extension(const std::string &path);
+void write_file_by_extension(const std::string &path, const std::string &content);
 
 // ----------------------------------------------------------------------------------------
 // Evaluator (evaluators.rs:98-224): measure parsing + a device plan for one view
@@ -189,7 +199,8 @@ class Evaluator {
 
     double mean_from_fx(int64_t fx) const;
     // evaluate_mean / evaluate_to_map for any model
-    double evaluate_mean(const Model &m, std::vector<double> *per_query = nullptr) const;
+    // (model_uid != 0: the model belongs to a CModel handle, its device form is cached)
+    double evaluate_mean(const Model &m, std::vector<double> *per_query = nullptr, uint64_t model_uid = 0) const;
     // C weight vectors at once
     std::vector<double> evaluate_linear(const std::vector<std::vector<double>> &ws) const;
 
@@ -264,6 +275,8 @@ struct CDataset {
 };
 struct CModel {
     frb::Model model;
+    uint64_t uid;  // identity of this (immutable) model for per-dataset device caches
+    explicit CModel(frb::Model m);
 };
 struct CQRel {
     std::shared_ptr<frb::QRel> qrel;

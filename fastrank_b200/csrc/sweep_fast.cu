@@ -573,11 +573,11 @@ int launch_fast(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStrea
 
 #include "sweep_packed.cuh"
 
-template <int TB, bool WS>
+template <int TB, bool WS, int MINB>
 int launch_packed(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStream_t stream) {
     const uint32_t dm8 = (a.dm + 7) & ~7u;
     const PackedLayout L(TB, WS ? dm8 * kMaxSweeps : 0u);
-    auto kernel = sweep_packed_kernel<TB, WS>;
+    auto kernel = sweep_packed_kernel<TB, WS, MINB>;
     static std::mutex mu;
     static std::map<std::pair<int, size_t>, int> cache;
     int occ = 0;
@@ -606,7 +606,6 @@ int launch_packed(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStr
     v.q_order = pl->fast.pk_q_order.p;
     v.tile_task_off = pl->fast.pk_tile_task_off.p;
     v.tasks = pl->fast.pk_tasks.p;
-    v.pd_cls = pl->fast.pd_cls.p;
     v.tbl = pl->fast.pk_tbl.p;
     v.tbl_r = pl->fast.tbl_r;
     v.n_cls = pl->fast.n_cls;
@@ -725,7 +724,8 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
     // sweep_packed_kernel: NDCG@k, k <= 16 ranks of 4 bits in one register per candidate
     fp.packed_ok = false;
     if (ndcg && fp.n_cls >= 1 && fp.n_cls <= 15 && pl->depth <= 16) {
-        std::vector<uint32_t> q_task_off{0}, pk_tile_off{0}, pk_tasks;
+        std::vector<uint32_t> q_task_off{0}, pk_tile_off{0};
+        std::vector<uint4> pk_tasks;
         std::vector<uint16_t> q_order(pq_local.size(), 0);
         std::vector<std::pair<uint64_t, uint16_t>> cost;
         for (uint32_t tile = 0; tile + 1 < tile_q_off.size(); ++tile) {
@@ -745,7 +745,10 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
                     while (run > 0) {
                         const uint32_t n = run >= 13 ? std::min<uint32_t>(run, 16) : (run > 8 ? 8 : run);
                         const uint32_t w = n > 8 ? 16 : (n > 4 ? 8 : 4);
-                        pk_tasks.push_back((start + i) | (n << 16));
+                        unsigned long long tags = 0;  // gain class + 1 of each document, 4 bits apiece
+                        for (uint32_t u = 0; u < n; ++u)
+                            tags |= (unsigned long long)(pd_cls[pq_doc0[pq] + i + u] + 1u) << (4 * u);
+                        pk_tasks.push_back(make_uint4((start + i) | (n << 16), (uint32_t)tags, (uint32_t)(tags >> 32), 0u));
                         qcost += (uint64_t)len * (3 + 2 * w) + (uint64_t)w * w;
                         i += n;
                         run -= n;
@@ -922,13 +925,26 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         if (const char *env = getenv("FASTRANK_WSMEM")) ws = atoi(env) != 0;
         int rc;
         if (use_packed) {
-            const bool wsp = PackedLayout(pl->tb, ((a.dm + 7) & ~7u) * kMaxSweeps).total <= (pl->tb == 128 ? 56u : 100u) * 1024;
-            if (pl->tb == 128)
-                rc = wsp ? launch_packed<128, true>(pl, a, n_groups, s) : launch_packed<128, false>(pl, a, n_groups, s);
-            else if (pl->tb == 256)
-                rc = wsp ? launch_packed<256, true>(pl, a, n_groups, s) : launch_packed<256, false>(pl, a, n_groups, s);
-            else
-                rc = wsp ? launch_packed<512, true>(pl, a, n_groups, s) : launch_packed<512, false>(pl, a, n_groups, s);
+            // resident CTAs per SM at 128 threads: 4 (<= 128 registers), 5 (<= 96) or 6 (<= 80)
+            int minb = 5;
+            if (const char *env = getenv("FASTRANK_PACKED_MINB")) minb = atoi(env);
+            const size_t pk_bytes = PackedLayout(pl->tb, ((a.dm + 7) & ~7u) * kMaxSweeps).total;
+            const size_t room = pl->tb == 128 ? (size_t)(226 * 1024) / (size_t)std::max(4, std::min(minb, 6)) - 1024
+                                              : (size_t)100 * 1024;
+            bool wsp = pk_bytes <= room;
+            if (const char *env = getenv("FASTRANK_WSMEM")) wsp = atoi(env) != 0;
+            if (pl->tb == 128) {
+                if (minb <= 4)
+                    rc = wsp ? launch_packed<128, true, 4>(pl, a, n_groups, s) : launch_packed<128, false, 4>(pl, a, n_groups, s);
+                else if (minb == 5)
+                    rc = wsp ? launch_packed<128, true, 5>(pl, a, n_groups, s) : launch_packed<128, false, 5>(pl, a, n_groups, s);
+                else
+                    rc = wsp ? launch_packed<128, true, 6>(pl, a, n_groups, s) : launch_packed<128, false, 6>(pl, a, n_groups, s);
+            } else if (pl->tb == 256) {
+                rc = wsp ? launch_packed<256, true, 2>(pl, a, n_groups, s) : launch_packed<256, false, 2>(pl, a, n_groups, s);
+            } else {
+                rc = wsp ? launch_packed<512, true, 1>(pl, a, n_groups, s) : launch_packed<512, false, 1>(pl, a, n_groups, s);
+            }
         } else if (pl->tb == 128) {
             if (ws)
                 rc = fp.td == 8 ? launch_fast<128, 8, true>(pl, a, n_groups, s)

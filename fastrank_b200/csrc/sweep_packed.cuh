@@ -23,14 +23,14 @@ struct PackedView {
     const uint32_t *q_task_off;     // [nq_plan + 1] first task of a plan query
     const uint16_t *q_order;        // [nq_plan] tile-local query indices, costliest first
     const uint32_t *tile_task_off;  // [nt + 1]
-    const uint32_t *tasks;          // t0 | n << 16 (tile-local documents of one query, n <= 16)
-    const uint8_t *pd_cls;          // plan doc -> gain class
+    const uint4 *tasks;             // .x = t0 | n << 16 (tile-local documents of one query, n <= 16),
+                                    // .y/.z = their tags (gain class + 1), 4 bits each, 0 beyond n
     const double *tbl;              // [n_cls + 1][tbl_r]: row 0 zeros (empty slot), row c + 1 = class c
     uint32_t tbl_r, n_cls;
 };
 
 struct PackedLayout {
-    size_t t2, sum, roww, tbl, qd, tasks, order, cls, rowsw, misc, w, total;
+    size_t t2, sum, roww, tbl, qd, tasks, order, rowsw, misc, w, total;
     __host__ __device__ PackedLayout(int tb, uint32_t w_doubles) {
         size_t o = 0;
         t2 = o;     o += sizeof(double2) * kMaxSweeps * (size_t)tb;
@@ -38,9 +38,8 @@ struct PackedLayout {
         roww = o;   o += sizeof(double) * kMaxRows;
         tbl = o;    o += sizeof(double) * 16 * 16;
         qd = o;     o += sizeof(uint2) * tb;
-        tasks = o;  o += sizeof(uint32_t) * tb;
+        tasks = o;  o += sizeof(uint4) * tb;
         order = o;  o += align16(sizeof(uint16_t) * tb);
-        cls = o;    o += align16(tb);
         rowsw = o;  o += kMaxRows;
         misc = o;   o += 256;
         w = o;      o += sizeof(double) * w_doubles;
@@ -55,12 +54,19 @@ __device__ __forceinline__ void count_pair(unsigned &ci, unsigned &cj, double si
         : "d"(sj), "d"(si));
 }
 
+// tag << (4 * rank), 0 when the rank is beyond the register (shl.b64 clamps the shift amount)
+__device__ __forceinline__ unsigned long long tag_at_rank(unsigned tag, unsigned rank) {
+    unsigned long long v;
+    asm("{ .reg .b64 t; cvt.u64.u32 t, %1; shl.b64 %0, t, %2; }" : "=l"(v) : "r"(tag), "r"(rank << 2));
+    return v;
+}
+
 // Ranks the W documents [t0, t0 + n) of the query occupying tile-local [qs, qe) under this lane's
-// candidate c and files their gain classes by rank into `packed` (ranks below lim only).
+// candidate c and files their tags by rank into `packed`: 4 bits per rank, ranks >= 16 fall off
+// the register and ranks in [lim, 16) are never read.  `tags` holds the chunk's tags, 0 beyond n.
 template <int W>
 __device__ __forceinline__ void rank_chunk(const double2 *__restrict__ trow, double c, int qs, int qe, int t0, int n,
-                                           unsigned lim, const uint8_t *__restrict__ s_cls,
-                                           unsigned long long &packed) {
+                                           unsigned long long tags, unsigned long long &packed) {
     double st[W];
     unsigned cnt[W];
 #pragma unroll
@@ -71,7 +77,7 @@ __device__ __forceinline__ void rank_chunk(const double2 *__restrict__ trow, dou
         cnt[i] = 0;
     }
     int jq = qs;
-#pragma unroll 2
+#pragma unroll 4
     for (; jq < t0; ++jq) {  // documents that win ties against the chunk's
         const double2 tx = trow[jq];
         const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
@@ -86,7 +92,7 @@ __device__ __forceinline__ void rank_chunk(const double2 *__restrict__ trow, dou
         }
     }
     jq = t0 + n;
-#pragma unroll 2
+#pragma unroll 4
     for (; jq < qe; ++jq) {  // documents that lose ties
         const double2 tx = trow[jq];
         const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
@@ -94,14 +100,11 @@ __device__ __forceinline__ void rank_chunk(const double2 *__restrict__ trow, dou
         for (int i = 0; i < W; ++i) count_gt(cnt[i], sj, st[i]);
     }
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
-        if (i < n && cnt[i] < lim)
-            packed |= (unsigned long long)((unsigned)s_cls[t0 + i] + 1u) << (cnt[i] << 2);
-    }
+    for (int i = 0; i < W; ++i) packed |= tag_at_rank((unsigned)(tags >> (4 * i)) & 15u, cnt[i]);
 }
 
-template <int TB, bool WS>
-__global__ void __launch_bounds__(TB, (TB == 128 ? 4 : (TB == 256 ? 2 : 1)))
+template <int TB, bool WS, int MINB>
+__global__ void __launch_bounds__(TB, MINB)
 sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NS = kMaxSweeps;
@@ -119,9 +122,8 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
     double *s_roww = (double *)(smem_raw + L.roww);
     double *s_tbl = (double *)(smem_raw + L.tbl);
     uint2 *s_qd = (uint2 *)(smem_raw + L.qd);
-    uint32_t *s_tasks = (uint32_t *)(smem_raw + L.tasks);
+    uint4 *s_tasks = (uint4 *)(smem_raw + L.tasks);
     uint16_t *s_order = (uint16_t *)(smem_raw + L.order);
-    uint8_t *s_cls = (uint8_t *)(smem_raw + L.cls);
     uint8_t *s_rowsw = (uint8_t *)(smem_raw + L.rowsw);
     int *s_misc = (int *)(smem_raw + L.misc);
     const double *__restrict__ wg = A.base_wt + (size_t)blockIdx.y * dm8 * NS;
@@ -181,7 +183,6 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
             s_qd[t] = make_uint2(P.pq_local[q0 + t], (tb0 - task0) | ((tb1 - tb0) << 16));
             s_order[t] = V.q_order[q0 + t];
         }
-        s_cls[t] = active ? __ldg(V.pd_cls + doc0 + t) : (uint8_t)0;
 
         // ---- phase 1: one pass over the tile's features for every sweep (as sweep_fast_kernel) ----
         {
@@ -271,14 +272,15 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
             const double2 *trow = s_t2 + (size_t)s_rowsw[rowc] * TB;
             unsigned long long packed = 0ull;
             for (int tk = tk0; tk < tk0 + ntk; ++tk) {
-                const uint32_t w = s_tasks[tk];
-                const int t0 = (int)(w & 0xffffu), n = (int)(w >> 16);
+                const uint4 w = s_tasks[tk];
+                const int t0 = (int)(w.x & 0xffffu), n = (int)(w.x >> 16);
+                const unsigned long long tags = (unsigned long long)w.y | ((unsigned long long)w.z << 32);
                 if (n > 8)
-                    rank_chunk<16>(trow, c, qs, qe, t0, n, lim, s_cls, packed);
+                    rank_chunk<16>(trow, c, qs, qe, t0, n, tags, packed);
                 else if (n > 4)
-                    rank_chunk<8>(trow, c, qs, qe, t0, n, lim, s_cls, packed);
+                    rank_chunk<8>(trow, c, qs, qe, t0, n, tags, packed);
                 else
-                    rank_chunk<4>(trow, c, qs, qe, t0, n, lim, s_cls, packed);
+                    rank_chunk<4>(trow, c, qs, qe, t0, n, tags, packed);
             }
             // fold: ranks 0 .. lim-1 in order (evaluators.rs:265-270); an empty slot adds +0.0 like a
             // zero-gain document does in the reference

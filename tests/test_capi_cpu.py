@@ -222,3 +222,54 @@ def test_libsvm_parser_cases(fr, tmp_path):
             _load_text(fr, tmp_path, text, name="bad.libsvm")
     with pytest.raises(Exception):
         fr.CDataset.open_ranksvm(str(tmp_path / "does-not-exist"))
+
+
+def _zstd_compress(data: bytes) -> bytes:
+    z = ctypes.CDLL("libzstd.so.1")
+    z.ZSTD_compressBound.restype = ctypes.c_size_t
+    z.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
+    z.ZSTD_compress.restype = ctypes.c_size_t
+    z.ZSTD_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+    cap = z.ZSTD_compressBound(len(data))
+    buf = ctypes.create_string_buffer(cap)
+    n = z.ZSTD_compress(buf, cap, data, len(data), 3)
+    return buf.raw[:n]
+
+
+def test_compressed_inputs_by_extension(fr, golden_dir, tmp_path):
+    """io_helper.rs:18-29: .gz (multi-member), .bz2 and .zst files are read transparently, for
+    datasets and for judgments."""
+    import bz2
+    import gzip
+
+    train = open(os.path.join(golden_dir, "trec_news_2018.train"), "rb").read()
+    qrel = open(os.path.join(golden_dir, "newsir18-entity.qrel"), "rb").read()
+    plain_ds = fr.CDataset.open_ranksvm(os.path.join(golden_dir, "trec_news_2018.train"))
+    plain_q = fr.CQRel.load_file(os.path.join(golden_dir, "newsir18-entity.qrel")).to_dict()
+    half = train.index(b"\n", len(train) // 2) + 1
+    codecs = {
+        ".gz": lambda b: gzip.compress(b),
+        ".bz2": lambda b: bz2.compress(b),
+    }
+    try:
+        _zstd_compress(b"probe")
+        codecs[".zst"] = _zstd_compress
+    except OSError:
+        pass
+    for ext, enc in codecs.items():
+        p = tmp_path / ("train.libsvm" + ext)
+        # two concatenated members / frames for gzip, like MultiGzDecoder accepts
+        p.write_bytes(enc(train[:half]) + enc(train[half:]) if ext == ".gz" else enc(train))
+        ds = fr.CDataset.open_ranksvm(str(p))
+        assert ds.num_instances() == plain_ds.num_instances() == 782
+        assert ds.instances_by_query() == plain_ds.instances_by_query()
+        assert ds.feature_ids() == plain_ds.feature_ids()
+        q = tmp_path / ("judgments.qrel" + ext)
+        q.write_bytes(enc(qrel))
+        assert fr.CQRel.load_file(str(q)).to_dict() == plain_q
+    bad = tmp_path / "broken.gz"
+    bad.write_bytes(b"\x1f\x8b\x08\x00 not really gzip")
+    with pytest.raises(Exception):
+        fr.CQRel.load_file(str(bad))
+    with pytest.raises(Exception, match="No such file"):
+        fr.CDataset.open_ranksvm(str(tmp_path / "missing.gz"))
