@@ -4,11 +4,11 @@ DenseDataset (BASELINE.json configs[1]; configs[2] when --gpus > 1: the same dat
 by query, one NCCL all-reduce of the metric sums per group of candidates).
 
 One STEP = one coordinate-ascent line search for each of the 8 restarts
-(coordinate_ascent.rs:131-177): group A (direction 0 + direction -1, 26 candidate weight
-vectors per restart) and group B (direction +1, 25 per restart) = 408 evaluate_mean
-equivalents (evaluators.rs:173-184), two calls of fr_dev_eval_coord_sweeps.  Every candidate is
-a full evaluation: all N documents scored with the reference's left-to-right f64 dot product,
-ranked inside their query, NDCG@10 per query, mean over queries.
+(coordinate_ascent.rs:131-177): direction 0, -1 and +1 = 51 candidate weight vectors per restart
+= 408 evaluate_mean equivalents (evaluators.rs:173-184) in ONE call of
+fr_dev_eval_coord_sweeps_fast = one kernel launch = one pass over X.  Every candidate is a full
+evaluation: all N documents scored, ranked inside their query, NDCG@10 per query, mean over
+queries.
 
   value      evaluations/s with the dataset resident in HBM (device-timed, CUDA events on the
              library's stream, max over ranks)
@@ -16,7 +16,12 @@ ranked inside their query, NDCG@10 per query, mean over queries.
              make_dense_dataset_f32_f64_i64 + train_model (CA, 8 restarts, to convergence);
              the upload of X/y/qid is inside the timed region, evaluations counted are the
              ones the reference's control flow consumes
-  roofline   dominant kernel (coord_sweep_kernel) vs the measured HBM copy bandwidth
+  roofline   dominant kernel (sweep_packed_kernel, the batched sweep for NDCG@k) vs the measured
+             HBM copy bandwidth, plus what actually bounds it (issue slots / FP64 pipe, from the
+             committed ncu capture)
+  side_trees / side_mslr (N = 1, after the timed region, not part of it)
+             BASELINE.json configs[3] (500 trees x depth 8 scored over the same 1M x 136) and
+             configs[4]'s shape (3 771 125 x 136 x 31 531 queries, the same CA step)
   cpu_baseline / --impl reference
              the CPU oracle (C restatement of the reference; the Rust reference cannot be
              built in this image) on the host cores, one thread per restart as the reference
@@ -54,6 +59,13 @@ LONG_TAIL = os.environ.get("FASTRANK_BENCH_TAIL", "") == "1"  # side experiment:
 if (N_DOCS, N_QUERIES) != (1_000_000, 30_000) or LONG_TAIL:
     WORKLOAD = "synthetic %d docs x 136 features x %d queries%s, coordinate_ascent 8 restarts, ndcg@10" % (
         N_DOCS, N_QUERIES, " (log-normal list lengths, up to 1300 documents)" if LONG_TAIL else "")
+
+
+def base_config(world: int) -> dict:
+    """The keys both arms print (the driver compares them)."""
+    return {"workload": WORKLOAD, "evals_per_step": EVALS_PER_STEP,
+            "l2": "inputs (544 MB feature matrix per sweep) larger than the 126 MB L2",
+            "parallelism": "query-sharded x%d" % world if world > 1 else "single GPU"}
 
 
 def log(*a):
@@ -227,13 +239,126 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "C restatement of the Rust reference (oracle/), not the Rust build"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": base_config(world),
+        "details": {"note": "C restatement of the Rust reference (oracle/), not the Rust build; one thread per "
+                            "restart as rayon does (coordinate_ascent.rs:216)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "threads": threads, "kind": "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:  # this arm is pure CPU: the CUDA library must not even be mapped
+        line["details"]["native_so_loaded"] = any("libfastrank_b200" in m for m in open("/proc/self/maps"))
+    except OSError:
+        pass
     print(json.dumps(line), file=JSON_OUT, flush=True)
 
+
+
+# ------------------------------------------------------------------------------------------
+# side measurements (single GPU, after the timed region): the other BASELINE.json configs
+# ------------------------------------------------------------------------------------------
+def random_tree(rng, X, depth, max_depth):
+    if depth >= max_depth or (depth > 2 and rng.random() < 0.05):
+        return {"LeafNode": float(np.round(rng.uniform(0, 4), 3))}
+    fid = int(rng.integers(0, X.shape[1]))
+    split = float(np.quantile(X[:2000, fid], rng.uniform(0.1, 0.9)))
+    return {"FeatureSplit": {"fid": fid, "split": split, "lhs": random_tree(rng, X, depth + 1, max_depth),
+                             "rhs": random_tree(rng, X, depth + 1, max_depth)}}
+
+
+def count_nodes(t):
+    if "LeafNode" in t:
+        return 1
+    return 1 + count_nodes(t["FeatureSplit"]["lhs"]) + count_nodes(t["FeatureSplit"]["rhs"])
+
+
+def side_trees(fr, X, y, qid, n_trees=500, depth=8, reps=5, cpu_docs=20000):
+    """BASELINE.json configs[3]: a 500-tree, depth-8 ensemble (model.rs:64-84, :104-112) scored over
+    the bench's 1M x 136 through the reference-facing API (CModel.predict_dense / evaluate_mean),
+    kernel time from CUDA events, the C oracle on a bounded sample of the same documents."""
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(4)
+    members = [{"DecisionTree": random_tree(rng, X, 1, depth)} for _ in range(n_trees)]
+    spec = {"Ensemble": {"weights": [1.0] * n_trees, "models": members}}
+    nodes = sum(count_nodes(m["DecisionTree"]) for m in members)
+    n = X.shape[0]
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    model = fr.CModel.from_dict(spec)
+    t0 = time.perf_counter()
+    scores = model.predict_dense(ds)  # uploads the dataset, lowers and uploads the forest
+    t_first = time.perf_counter() - t0
+    ds.device_profile(enable=True, read=True)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        scores = model.predict_dense(ds)
+    t_predict = (time.perf_counter() - t0) / reps
+    n_k, k_ms = ds.device_profile(read=True)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        mean = ds.evaluate_mean(model, "ndcg@10")
+    t_eval = (time.perf_counter() - t0) / reps
+    ds.device_profile(enable=False, read=True)
+    t0 = time.perf_counter()
+    exp = orc.score_model(X[:cpu_docs], spec)
+    t_cpu = time.perf_counter() - t0
+    kernel_ms = k_ms / max(n_k, 1)
+    algo = n * X.shape[1] * 4 + n * 8 + nodes * 16  # SURVEY 8(d): X + scores out + nodes
+    visits = float(n) * n_trees * (depth - 1)
+    peak = measured_peak_gbs()[0]
+    return {"workload": "%d trees, depth <= %d (%d nodes), scored over %d x %d" % (n_trees, depth, nodes, n, X.shape[1]),
+            "kernel": "forest_heap_kernel", "kernel_ms": kernel_ms, "predict_dense_api_ms": 1e3 * t_predict,
+            "evaluate_mean_api_ms": 1e3 * t_eval, "first_call_ms": 1e3 * t_first,
+            "docs_per_s_kernel": n / (kernel_ms / 1e3) if kernel_ms > 0 else None,
+            "docs_per_s_api": n / t_predict, "node_visits_per_s": visits / (kernel_ms / 1e3) if kernel_ms > 0 else None,
+            "algorithmic_bytes": algo, "achieved_GBps": algo / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else None,
+            "frac_of_hbm_peak": algo / (kernel_ms / 1e3) / 1e9 / peak if kernel_ms > 0 else None,
+            "ndcg10": mean, "cpu_oracle_docs_per_s_1thread": cpu_docs / t_cpu,
+            "bit_exact_vs_oracle": bool(np.array_equal(scores[:cpu_docs], exp)), "bit_exact_sample_docs": cpu_docs}
+
+
+def side_mslr(steps=5, warmup=3):
+    """BASELINE.json configs[4]'s shape: 3 771 125 x 136 documents in 31 531 queries (~120 per
+    query, MSLR-WEB30K-like), the same coordinate-ascent step (8 restarts x 51 candidates, NDCG@10)."""
+    from fastrank_b200._native import ffi, lib
+    from fastrank_b200.kernels import DevDataset, dense_query_index
+
+    n, q = 3_771_125, 31_531
+    X, y, qid = make_data(n, N_FEAT, q)
+    qidx, nq = dense_query_index(qid)
+    dev = DevDataset(X, y.astype(np.float32), qidx, nq)
+    try:
+        plan = dev.plan(0, DEPTH)
+        packed = []
+        for s in range(warmup + steps):
+            base, fids, ga, gb = step_inputs(s, N_FEAT)
+            packed.append(plan.pack_sweeps(base, fids, [a + b for a, b in zip(ga, gb)]))
+        for s in range(warmup):
+            plan.coord_sweeps_packed(packed[s])
+        dev.profile(True)
+        dev.profile_read(reset=True)
+        dev.timer_start()
+        for s in range(steps):
+            plan.coord_sweeps_packed(packed[warmup + s])
+        ms = dev.timer_stop()
+        n_k, k_ms = dev.profile_read(reset=True)
+        dev.profile(False)
+        algo = n * N_FEAT * 4 + n * 5 + nq * 16 + N_RESTARTS * N_FEAT * 8 + EVALS_PER_STEP * 16
+        kernel_ms = k_ms / max(n_k, 1)
+        peak = measured_peak_gbs()[0]
+        return {"workload": "synthetic %d docs x %d features x %d queries, coordinate_ascent 8 restarts, ndcg@10" % (n, N_FEAT, q),
+                "kernel": ffi.string(lib.fr_dev_plan_sweep_kernel(plan.ptr)).decode(),
+                "tile_documents": int(lib.fr_dev_plan_tile_documents(plan.ptr)),
+                "untiled_queries": int(lib.fr_dev_plan_untiled_queries(plan.ptr)),
+                "ms_per_step": ms / steps, "evals_per_s": EVALS_PER_STEP * steps / (ms / 1e3), "steps": steps,
+                "kernel_ms_per_launch": kernel_ms, "launches_per_step": n_k / steps,
+                "algorithmic_bytes_per_launch": algo, "achieved_GBps": algo / (kernel_ms / 1e3) / 1e9,
+                "frac_of_hbm_peak": algo / (kernel_ms / 1e3) / 1e9 / peak,
+                "bf16_gemm_variant": "not built: phase 1 (the 8-column X.W product a GEMM would replace) is a minor "
+                                     "share of this launch, see profiles/ and DESIGN.md"}
+    finally:
+        dev.close()
 
 # ------------------------------------------------------------------------------------------
 # GPU arm
@@ -244,7 +369,7 @@ def run_ours(args, rank, world, local_rank):
 
     import fastrank_b200 as fr
     from fastrank_b200 import dist as frdist
-    from fastrank_b200._native import lib
+    from fastrank_b200._native import ffi, lib
     from fastrank_b200.kernels import DevDataset, dense_query_index
 
     if lib.fr_dev_device_count() <= 0:
@@ -340,6 +465,22 @@ def run_ours(args, rank, world, local_rank):
         ms = float(t.item())
     value = EVALS_PER_STEP * args.steps / (ms / 1e3)
 
+    # multi-GPU parity, visible to the driver: the sharded sums of the first timed step (already
+    # all-reduced: identical on every rank) against a single-GPU plan over rank 0's FULL copy
+    dist_equal = None
+    if world > 1 and not args.exact:
+        sharded = plan.coord_sweeps_packed(packed[args.warmup][0]).copy()
+        if rank == 0:
+            qidx_full, nq_full = dense_query_index(qid)
+            dev1 = DevDataset(X, y.astype(np.float32), qidx_full, nq_full, device=local_rank)
+            try:
+                plan1 = dev1.plan(0, DEPTH)
+                base, fids, ga, gb = step_inputs(args.warmup, d)
+                single = plan1.coord_sweeps_packed(plan1.pack_sweeps(base, fids, [a + b for a, b in zip(ga, gb)]))
+                dist_equal = bool(np.array_equal(single, sharded))
+            finally:
+                dev1.close()
+
     # roofline of the dominant kernel.  One launch of the batched sweep = ONE pass over this
     # rank's slice of the feature matrix serving all 8 restarts (204 or 200 candidates):
     # algorithmic bytes = X + per-document plan data (position 4 B, gain class 1 B) +
@@ -351,8 +492,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         bytes_per_launch = (n_local * d * 4 + n_local * 5 + nq_local * 16 + N_RESTARTS * d * 8
                             + EVALS_PER_STEP // launches_per_step * 16)
-        tile = int(lib.fr_dev_plan_tile_documents(plan.ptr))
-        kname = "sweep_fast_kernel<%d,8,%s>" % (tile, "true" if tile == 128 else "false")
+        kname = ffi.string(lib.fr_dev_plan_sweep_kernel(plan.ptr)).decode()
     avg_launch_ms = kern_ms / max(n_kern, 1)
     achieved = bytes_per_launch / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else 0.0
     peak, peak_src = measured_peak_gbs()
@@ -393,10 +533,18 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_s = time.perf_counter() - t0
     stats = fr.query_json("last_train_stats")
+    import hashlib
+
+    weights = np.asarray(model.to_dict()["Linear"]["weights"], dtype=np.float64)
+    weights_sha = hashlib.sha256(weights.tobytes()).hexdigest()
+    weights_same = None
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+        digests = [None] * world
+        dist.all_gather_object(digests, weights_sha)
+        weights_same = len(set(digests)) == 1
     cand_per_sweep = 1 + 2 * T_ITERS  # both direction groups ride in one submission
     h2d_total = Xl.nbytes + yl.nbytes + ql.nbytes + stats["sweeps"] * (d * 8 + cand_per_sweep * 16 + 4)
     d2h_total = stats["sweeps"] * cand_per_sweep * 8
@@ -407,7 +555,8 @@ def run_ours(args, rank, world, local_rank):
            "global_steps": stats["global_steps"], "final_train_ndcg10": final,
            "seconds_from_numpy": t_from_numpy, "seconds_train_model": t_train, "seconds_evaluate": t_eval,
            "train_seconds_setup": stats.get("seconds_setup"), "train_seconds_device": stats.get("seconds_device"),
-           "sweeps": stats["sweeps"],
+           "sweeps": stats["sweeps"], "trained_weights_sha256": weights_sha,
+           "trained_weights_identical_on_all_ranks": weights_same,
            "what": "from_numpy + train_model(CA, 8 restarts, seed 42, to convergence) + evaluate through the C ABI"}
     del ds, model
     clocks = sampler.stop()  # sampled across both timed regions (device-timed steps and e2e)
@@ -418,7 +567,7 @@ def run_ours(args, rank, world, local_rank):
         threads = min(N_RESTARTS, os.cpu_count() or 1)
         per_thread = args.cpu_evals_per_thread
         v, dt = cpu_evals_per_sec(X, y, qid, per_thread, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "threads": threads, "kind": "port",
                "sample": "%d threads x %d full evaluate_mean (1M docs, ndcg@10) with the C oracle, %.1fs" % (threads, per_thread, dt)}
 
     if rank == 0:
@@ -426,15 +575,25 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "evals_per_step": EVALS_PER_STEP,
-                       "l2": "inputs (544 MB feature matrix per sweep) larger than the 126 MB L2",
-                       "parallelism": "query-sharded x%d" % world if world > 1 else "single GPU",
-                       "wall_ms_per_step": wall_ms / max(args.steps, 1),
-                       "tile_documents": plan_layout[0], "untiled_queries": plan_layout[1]},
+            "config": base_config(world),
+            "details": {"wall_ms_per_step": wall_ms / max(args.steps, 1), "tile_documents": plan_layout[0],
+                        "untiled_queries": plan_layout[1]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }
+        if dist_equal is not None:
+            line["dist_sums_equal_single_gpu"] = dist_equal
         if full_rescore:
             line["roofline_full_rescore"] = full_rescore
+        if world == 1 and not args.no_side:
+            try:
+                line["side_trees"] = side_trees(fr, X, y, qid)
+            except Exception as e:  # a side measurement must not cost the headline line
+                line["side_trees"] = {"error": repr(e)}
+            del X, Xl
+            try:
+                line["side_mslr"] = side_mslr()
+            except Exception as e:
+                line["side_mslr"] = {"error": repr(e)}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), file=JSON_OUT, flush=True)
@@ -462,6 +621,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip side_trees / side_mslr (BASELINE configs[3], [4])")
     ap.add_argument("--two-launches", action="store_true",
                     help="submit direction +1 separately (no speculation): two launches per step")
     ap.add_argument("--exact", action="store_true", help="time the exact-order sweep kernel instead of the batched one")

@@ -341,6 +341,16 @@ class CDataset(_Handle):
     def predict_scores(self, model: CModel) -> Dict[int, float]:
         return model.predict_scores(self)
 
+    def device_profile(self, enable: Optional[bool] = None, read: bool = False):
+        """Per-kernel device timing of this dataset's scoring / ranking launches (CUDA events on
+        the library's stream).  enable=True/False switches it; read=True returns
+        (launches, total_ms) since the last read and resets the record."""
+        self._require_init()
+        n = ffi.new("uint64_t*") if read else ffi.NULL
+        ms = ffi.new("double*") if read else ffi.NULL
+        _check_fast_path(lib.dataset_device_profile(self.pointer, -1 if enable is None else int(bool(enable)), n, ms))
+        return (int(n[0]), float(ms[0])) if read else None
+
     def predict_trecrun(self, model: CModel, output_path: str, system_name: str = "fastrank",
                         quiet=True, depth=0) -> int:
         self._require_init()

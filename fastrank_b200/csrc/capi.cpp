@@ -423,6 +423,27 @@ const void *evaluate_mean_f64(const CModel *model, const CDataset *dataset, cons
     }
 }
 
+const void *dataset_device_profile(const CDataset *dataset, int enable, uint64_t *out_launches,
+                                   double *out_total_ms) {
+    try {
+        const CDataset &d = need(dataset);
+        ParentDataset &p = *d.view.parent;
+        fr_dev_dataset *dev = p.device();
+        std::lock_guard<std::recursive_mutex> lock(p.use_mu);
+        if (enable >= 0 && fr_dev_profile_enable(dev, enable)) throw Error(fr_dev_last_error());
+        if (out_launches || out_total_ms) {
+            uint64_t n = 0;
+            double ms = 0.0;
+            if (fr_dev_profile_read(dev, &n, &ms, 1)) throw Error(fr_dev_last_error());
+            if (out_launches) *out_launches = n;
+            if (out_total_ms) *out_total_ms = ms;
+        }
+        return nullptr;
+    } catch (const std::exception &e) {
+        return dup_cstr(error_json(e.what()));
+    }
+}
+
 const void *predict_to_trecrun(const CModel *model, const CDataset *dataset, const void *output_path,
                                const void *system_name, size_t depth) {
     return json_call([&]() -> std::string {  // json_api.rs:75-120

@@ -784,6 +784,14 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
 
 extern "C" int fr_dev_plan_has_fast_sweep(const fr_dev_plan *plan) { return plan && plan->fast.ok ? 1 : 0; }
 
+extern "C" const char *fr_dev_plan_sweep_kernel(const fr_dev_plan *plan) {
+    if (!plan || !plan->fast.ok) return "";
+    bool packed = plan->fast.packed_ok;
+    if (const char *env = getenv("FASTRANK_SWEEP_KERNEL")) packed = packed && std::string(env) != "tile";
+    if (packed) return plan->tb == 128 ? "sweep_packed_kernel<128>" : plan->tb == 256 ? "sweep_packed_kernel<256>" : "sweep_packed_kernel<512>";
+    return plan->tb == 128 ? "sweep_fast_kernel<128,8>" : plan->tb == 256 ? "sweep_fast_kernel<256,8>" : "sweep_fast_kernel<512,8>";
+}
+
 extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, const double *base_w,
                                              size_t wlen, const uint32_t *fid, const double *cand_w,
                                              const uint32_t *n_cand, size_t cand_stride,

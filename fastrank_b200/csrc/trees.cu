@@ -338,18 +338,24 @@ int launch_forest(fr_dev_dataset *ds, const fr_dev_model *m, double *out_pos, do
         const size_t hsmem = smem + 2 * (size_t)fo.batch * (16u << fo.levels);
         if (hsmem > 48 * 1024)
             CU(cudaFuncSetAttribute(forest_heap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+        auto *ev = ds->prof_slot();
+        if (ev) cudaEventRecord(ev->first, stream);
         forest_heap_kernel<<<grid, kTile, hsmem, stream>>>(ds->x.p, ds->ld, fo.dstage, ds->n, fo.heap_blocks.p,
                                                            fo.weights.p, fo.n_trees, fo.levels, fo.batch,
                                                            fo.weighted ? 1 : 0, ds->inst_of_pos_dev.p, out_pos,
                                                            out_inst);
+        if (ev) cudaEventRecord(ev->second, stream);
         LAUNCHED();
         CU(cudaGetLastError());
         return 0;
     }
+    auto *ev = ds->prof_slot();
+    if (ev) cudaEventRecord(ev->first, stream);
     forest_tile_kernel<<<grid, kTile, smem, stream>>>(ds->x.p, ds->ld, fo.dstage, ds->n, fo.nodes.p,
                                                       fo.roots.p, fo.weights.p, fo.n_trees, fo.levels,
                                                       fo.weighted ? 1 : 0, ds->inst_of_pos_dev.p, out_pos,
                                                       out_inst);
+    if (ev) cudaEventRecord(ev->second, stream);
     LAUNCHED();
     CU(cudaGetLastError());
     return 0;

@@ -97,6 +97,15 @@ const void *predict_dense_f64(const CModel *model, const CDataset *dataset, doub
 const void *evaluate_mean_f64(const CModel *model, const CDataset *dataset, const CQRel *qrel,
                               const void *evaluator, double *out_mean);
 
+/* Device-side timing for reports (bench.py): brackets every scoring / ranking kernel this
+ * dataset launches with CUDA events on the library's stream (fr_dev_profile_* below, reached
+ * through the reference-facing handle).  enable: 1 on, 0 off, -1 leave as is; when out_launches /
+ * out_total_ms are non-NULL they receive the launches bracketed since the last call and the sum
+ * of their durations, and the record is reset.  Returns NULL on success, else an error JSON
+ * string (free_str). */
+const void *dataset_device_profile(const CDataset *dataset, int enable, uint64_t *out_launches,
+                                   double *out_total_ms);
+
 /* ======================================================================================
  * (2) Kernel ABI
  * ==================================================================================== */
@@ -200,6 +209,11 @@ int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *plan, size_t n_sweeps, const doub
                                   double *out_per_query);
 /* 1 when the batched sweep serves this plan (see above). */
 int fr_dev_plan_has_fast_sweep(const fr_dev_plan *plan);
+/* Name of the kernel that serves fr_dev_eval_coord_sweeps_fast on this plan (static string):
+ * "sweep_packed_kernel<TILE>" for NDCG@k with k <= 16 and at most 15 gain classes (a candidate's
+ * top-k kept in one 64-bit register), "sweep_fast_kernel<TILE,8>" otherwise, "" when the plan
+ * has no batched sweep.  For reports (bench.py roofline.kernel). */
+const char *fr_dev_plan_sweep_kernel(const fr_dev_plan *plan);
 
 /* Flattened ModelEnum (model.rs:10-16).  `code` is a postfix program of 64-bit words; see
  * fastrank_b200/csrc/model_program.hpp for the encoding produced by the host. */

@@ -46,7 +46,14 @@ def fx_sum(values) -> int:
     return int(np.rint(np.asarray(values, dtype=np.float64) * FX).astype(np.int64).sum())
 
 
-from fastrank_b200.kernels import DevDataset, DevPlan  # noqa: E402,F401
+def __getattr__(name):
+    # the kernel wrappers dlopen libfastrank_b200.so: loaded on first use only, so that code which
+    # needs the generator alone (bench.py --impl reference) never maps the CUDA library
+    if name in ("DevDataset", "DevPlan"):
+        from fastrank_b200 import kernels
+
+        return getattr(kernels, name)
+    raise AttributeError(name)
 
 
 def dense_qidx(qid):

@@ -23,7 +23,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["unit"] == "evals/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"]
+    assert set(d["config"]) == {"workload", "evals_per_step", "l2", "parallelism"}  # same keys as the GPU arm
+    assert d["details"]["native_so_loaded"] is False
 
 
 def test_gpu_arm_refuses_without_a_device():
