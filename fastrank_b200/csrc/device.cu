@@ -24,6 +24,7 @@
 #include <thread>
 
 #include "device_common.cuh"
+#include "tma.cuh"
 
 // =========================================================================================
 // Kernels
@@ -430,6 +431,124 @@ __global__ void __launch_bounds__(TB) linear_batch_kernel(PlanView P, BatchArgs 
     if (t < K) atomicAdd((unsigned long long *)(A.sums + t), s_sum[t]);
 }
 
+// The same evaluation with the tile's slice of X moved by the TMA copy engine (cp.async.bulk
+// completing on mbarriers, SASS UBLKCP) through a ring of kStages x kFB feature rows in shared
+// memory.  What it buys over linear_batch_kernel: the copies of the NEXT tile are already in
+// flight while this tile is ranked (rank_and_metric issues no loads of X), so a CTA keeps HBM
+// requests outstanding through all its phases instead of only while it scores, and a thread's
+// registers hold no staged feature values.  Needs tiles whose documents occupy consecutive
+// positions (any plan over a whole dataset or over whole queries of it): a feature row of the
+// tile is then ONE bulk copy of <= 544 bytes, started at the 16-byte boundary below the tile's
+// first position.  Warp 0 drives the copy engine kStages - 1 blocks ahead of the consumers (lane u
+// issues the copy of row u of the block); a stage is handed back through an "empty" mbarrier
+// (one arrival per warp).
+constexpr int kRowF = 128 + 8;  // floats per staged row: 128 documents + alignment slack, 16-byte multiple
+
+// kFB = feature rows per stage (one bulk copy each, issued by kFB lanes of warp 0), kStages = ring depth
+template <int KC, int kFB, int kStages>
+__global__ void __launch_bounds__(128) linear_tma_kernel(PlanView P, BatchArgs A) {
+    constexpr int TB = 128;
+    extern __shared__ __align__(16) unsigned long long smem[];
+    unsigned long long *s_sum = eval_sum_ptr<KC>(smem, TB);
+    char *extra = reinterpret_cast<char *>(smem) + eval_smem_bytes_c(KC, TB);
+    float *ring = reinterpret_cast<float *>(extra);                                    // [kStages][kFB][kRowF]
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + kStages * kFB * kRowF);       // [kStages]
+    uint64_t *empty = full + kStages;                                                  // [kStages]
+    double *s_w = reinterpret_cast<double *>(empty + kStages);                         // [dm][KC]
+    const int t = threadIdx.x, lane = t & 31;
+    const int K = A.K;
+    const uint32_t dm = A.dm;
+    const uint32_t nblk = (dm + kFB - 1) / kFB;
+    if (t < KC) s_sum[t] = 0ull;
+    for (uint32_t i = t; i < dm * KC; i += TB) s_w[i] = __ldg(A.wt + i);
+    if (t == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], TB / 32);
+        }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    const uint32_t my_tiles = blockIdx.x < P.nt ? (P.nt - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const uint32_t total_blocks = my_tiles * nblk;
+    // producer (warp 0): block g of this CTA = feature rows [b * kFB, ...) of its k-th tile
+    auto issue = [&](uint32_t g) {
+        const uint32_t k = g / nblk, b = g - k * nblk;
+        const uint32_t tile = blockIdx.x + k * gridDim.x;
+        const uint32_t doc0 = P.tile_doc_off[tile];
+        const uint32_t nd = P.tile_doc_off[tile + 1] - doc0;
+        const uint32_t pos0 = P.pd_pos[doc0];
+        const uint32_t a0 = pos0 & ~3u;
+        const uint32_t bytes = (((pos0 - a0) + nd) * 4u + 15u) & ~15u;
+        const uint32_t stage = g % kStages, use = g / kStages;
+        if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1u);
+        const uint32_t j0 = b * kFB, rows = min((uint32_t)kFB, dm - j0);
+        if (lane == 0) mbar_expect_tx(&full[stage], bytes * rows);
+        __syncwarp();
+        if ((uint32_t)lane < rows)
+            bulk_copy_g2s(ring + ((size_t)stage * kFB + lane) * kRowF, P.x + (size_t)(j0 + lane) * P.ld + a0, bytes,
+                          &full[stage]);
+    };
+    if (t < 32)
+        for (uint32_t g = 0; g + 1 < (uint32_t)kStages && g < total_blocks; ++g) issue(g);
+    uint32_t g = 0;
+    for (uint32_t tile = blockIdx.x; tile < P.nt; tile += gridDim.x) {
+        const uint32_t doc0 = P.tile_doc_off[tile];
+        const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
+        const bool active = t < nd;
+        const uint32_t pos0 = P.pd_pos[doc0];
+        const uint32_t pos = pos0 + (active ? (uint32_t)t : 0u);
+        const uint32_t qp = active ? P.pd_q[doc0 + t] : 0u;
+        const uint32_t off = (pos0 & 3u) + (active ? (uint32_t)t : 0u);
+        double tk[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) tk[k] = 0.0;
+        for (uint32_t b = 0; b < nblk; ++b, ++g) {
+            if (t < 32 && g + kStages - 1 < total_blocks) issue(g + kStages - 1);
+            const uint32_t stage = g % kStages;
+            mbar_wait(&full[stage], (g / kStages) & 1u);
+            const float *row = ring + (size_t)stage * kFB * kRowF + off;
+            const uint32_t j0 = b * kFB;
+            if (j0 + kFB <= dm) {
+                float xv[kFB];
+#pragma unroll
+                for (int u = 0; u < kFB; ++u) xv[u] = row[u * kRowF];
+#pragma unroll
+                for (int u = 0; u < kFB; ++u) {
+                    const double xd = (double)xv[u];
+                    const double *wj = s_w + (size_t)(j0 + u) * KC;
+#pragma unroll
+                    for (int k = 0; k < KC; k += 2) {
+                        const double2 w2 = *reinterpret_cast<const double2 *>(wj + k);
+                        tk[k] = __dadd_rn(tk[k], __dmul_rn(xd, w2.x));
+                        tk[k + 1] = __dadd_rn(tk[k + 1], __dmul_rn(xd, w2.y));
+                    }
+                }
+            } else {
+                for (uint32_t u = 0; j0 + u < dm; ++u) {
+                    const double xd = (double)row[u * kRowF];
+                    const double *wj = s_w + (size_t)(j0 + u) * KC;
+#pragma unroll
+                    for (int k = 0; k < KC; k += 2) {
+                        const double2 w2 = *reinterpret_cast<const double2 *>(wj + k);
+                        tk[k] = __dadd_rn(tk[k], __dmul_rn(xd, w2.x));
+                        tk[k + 1] = __dadd_rn(tk[k + 1], __dmul_rn(xd, w2.y));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);  // this warp is done with the stage
+        }
+        if (!active) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) tk[k] = 0.0;
+        }
+        rank_and_metric<KC>(P, tile, TB, t, active, qp, pos, tk, K, smem, A.perq, A.err);
+    }
+    if (t < K) atomicAdd((unsigned long long *)(A.sums + t), s_sum[t]);
+}
+
 // Rank + metric for scores that already sit in HBM (scores[position]); used after the model
 // interpreter (trees, ensembles, single-feature models).
 template <int TB>
@@ -628,7 +747,46 @@ int launch_sweep(fr_dev_plan *pl, int kc, int tb, uint32_t n_sweeps, const Sweep
     return 0;
 }
 
+template <int KC, int kFB, int kStages>
+int launch_linear_tma_cfg(fr_dev_plan *pl, const BatchArgs &args, cudaStream_t stream) {
+    const size_t smem = eval_smem_bytes(KC, 128) + sizeof(float) * kStages * kFB * kRowF + 16 * kStages +
+                        sizeof(double) * (size_t)std::max<uint32_t>(args.dm, 1) * KC;
+    uint32_t gx = 1;
+    if (grid_for(linear_tma_kernel<KC, kFB, kStages>, 128, smem, pl->sm_count, pl->nt, 1, &gx)) return 1;
+    auto *ev = pl->ds->prof_slot();
+    if (ev) cudaEventRecord(ev->first, stream);
+    linear_tma_kernel<KC, kFB, kStages><<<gx, 128, smem, stream>>>(pl->view(), args);
+    if (ev) cudaEventRecord(ev->second, stream);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <int KC>
+int launch_linear_tma(fr_dev_plan *pl, const BatchArgs &args, cudaStream_t stream) {
+    int cfg = 0;
+    if (const char *env = getenv("FASTRANK_TMA_EVAL_CFG")) cfg = atoi(env);  // tuning knob
+    if (cfg == 1) return launch_linear_tma_cfg<KC, 8, 4>(pl, args, stream);
+    if (cfg == 2) return launch_linear_tma_cfg<KC, 16, 3>(pl, args, stream);
+    if (cfg == 3) return launch_linear_tma_cfg<KC, 16, 4>(pl, args, stream);
+    if (cfg == 4) return launch_linear_tma_cfg<KC, 8, 6>(pl, args, stream);
+    return launch_linear_tma_cfg<KC, 8, 3>(pl, args, stream);
+}
+
 int launch_batch(fr_dev_plan *pl, int kc, int tb, const BatchArgs &args_in, cudaStream_t stream) {
+    // FASTRANK_TMA_EVAL=1: tiles of consecutive positions, up to 8 weight vectors, X through the TMA
+    // ring.  Off by default -- measured on B200 (1M x 136, tools/bench_evaluate.py): 0.152 ms per
+    // pass against 0.140 ms for the register-pipelined loads below (C = 1; 0.33 vs 0.28 at C = 8):
+    // the ring costs resident CTAs (9 -> 5 per SM), and it is the interleaving of many CTAs'
+    // score / rank phases, not the load path, that keeps HBM busy here (tools/micro/read_pattern.cu:
+    // this tile pattern reads at 6.1 TB/s with plain blocked LDGs).
+    const char *tma_env = getenv("FASTRANK_TMA_EVAL");
+    if (tma_env && atoi(tma_env) != 0 && pl->contiguous && tb == 128 && kc <= 8 && args_in.dm >= 1 &&
+        (size_t)args_in.dm * kc * sizeof(double) <= 32768) {
+        if (kc == 2) return launch_linear_tma<2>(pl, args_in, stream);
+        if (kc == 4) return launch_linear_tma<4>(pl, args_in, stream);
+        return launch_linear_tma<8>(pl, args_in, stream);
+    }
     // the weights of up to 32 KB worth of features are staged in shared memory at a time
     BatchArgs args = args_in;
     args.wchunk = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(args.dm, 1),
@@ -950,6 +1108,14 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
     if (tile_q_off.back() != pq_local.size() || tile_doc_off.back() != pd_pos.size()) close_tile();
     pl->nt = (uint32_t)tile_doc_off.size() - 1;
     pl->nq_plan = (uint32_t)pq_local.size();
+    // tiles whose documents sit at consecutive positions can be fetched row by row with bulk copies
+    pl->contiguous = true;
+    for (uint32_t tile = 0; tile < pl->nt && pl->contiguous; ++tile)
+        for (uint32_t k = tile_doc_off[tile] + 1; k < tile_doc_off[tile + 1]; ++k)
+            if (pd_pos[k] != pd_pos[k - 1] + 1) {
+                pl->contiguous = false;
+                break;
+            }
     // 3. discount table with the host libm (evaluators.rs:269: log2(i + 2))
     std::vector<double> lg2(std::max<uint32_t>(std::max(max_len, longest), 1));
     for (size_t i = 0; i < lg2.size(); ++i) lg2[i] = std::log2((double)i + 2.0);

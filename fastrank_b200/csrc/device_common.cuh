@@ -320,6 +320,7 @@ struct fr_dev_plan {
     int tb = 128;
     uint32_t nq_view = 0, nq_plan = 0, nt = 0;
     uint32_t max_len = 0;
+    bool contiguous = false;  // every tile covers consecutive positions (bulk-copy friendly)
     DevBuf<double> lg2;
     DevBuf<uint32_t> tile_doc_off, tile_q_off, pd_pos, pd_q, pq_local, pq_doc0, pq_view;
     DevBuf<double> pq_norm;

@@ -22,6 +22,7 @@
 
 #include "device_common.cuh"
 #include "model_program.hpp"
+#include "tma.cuh"
 
 namespace {
 
@@ -95,35 +96,6 @@ __global__ void __launch_bounds__(kTile) forest_tile_kernel(const float *__restr
 // 512-byte bulk copy per feature row) and the trees (double-buffered 16 KB batches) are moved by
 // the TMA copy engine (cp.async.bulk completing on mbarriers; one elected thread issues them), so
 // a walk never waits on L2: every step is two shared-memory reads (node, feature) and a compare.
-// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier -----------------
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
-}
-
 __global__ void __launch_bounds__(kTile) forest_heap_kernel(const float *__restrict__ x, size_t ld,
                                                             uint32_t dstage, size_t n,
                                                             const uint4 *__restrict__ heap,

@@ -18,8 +18,14 @@ def _mk(oracle, n, d, q, seed, shuffle=False):
     return X, y, qid, ods, dev
 
 
-@pytest.mark.parametrize("shuffle", [False, True])
-def test_linear_batch_bit_exact(oracle, shuffle):
+@pytest.mark.parametrize("shuffle,tma", [(False, False), (True, False), (False, True), (True, True)])
+def test_linear_batch_bit_exact(oracle, shuffle, tma, monkeypatch):
+    # tma: the same evaluation with X staged by TMA bulk copies (linear_tma_kernel, FASTRANK_TMA_EVAL=1;
+    # 11 vectors are served as one pass of 8 through the ring and one of 4)
+    if tma:
+        monkeypatch.setenv("FASTRANK_TMA_EVAL", "1")
+    else:
+        monkeypatch.delenv("FASTRANK_TMA_EVAL", raising=False)
     X, y, qid, ods, dev = _mk(oracle, 6000, 24, 180, seed=3, shuffle=shuffle)
     rng = np.random.default_rng(0)
     W = rng.normal(size=(11, 24))

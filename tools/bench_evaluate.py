@@ -31,25 +31,33 @@ def main():
     dev = DevDataset(X, y.astype(np.float32), qidx, nq, device=0)
     plan = dev.plan(0, 10)
     rng = np.random.default_rng(11)
-    for c in [int(v) for v in os.environ.get("CANDS", "1,8,26").split(",")]:
-        W = rng.normal(size=(c, d))
-        plan.eval_linear(W, per_query=False)
-        dev.profile(True)
-        dev.profile_read(reset=True)
-        for _ in range(reps):
-            sums, _ = plan.eval_linear(W, per_query=False)
-        launches, ms = dev.profile_read(reset=True)
-        dev.profile(False)
-        per_pass_ms = ms / reps
-        algo = n * d * 4 + n * 4 + (q + 1) * 4 + c * d * 8 + c * 8
-        print(json.dumps({
-            "workload": "full rescore, %d weight vectors per pass over %d x %d, ndcg@10" % (c, n, d),
-            "launches_per_pass": launches / reps, "ms_per_pass": per_pass_ms,
-            "evals_per_s": c / per_pass_ms * 1e3,
-            "algorithmic_bytes_per_pass": algo, "achieved_GBps": algo / per_pass_ms / 1e6,
-            "peak_GBps": peak, "frac": algo / per_pass_ms / 1e6 / peak,
-            "mean_ndcg10_first": float(sums[0]) * 2.0 ** -40 / nq,
-        }))
+    settings = sys.argv[1:] or [""]  # e.g. "FASTRANK_TMA_EVAL=1 FASTRANK_TMA_EVAL_CFG=2" (read per call)
+    for setting in settings:
+      pairs = [kv.split("=", 1) for kv in setting.split() if "=" in kv]
+      for k, v in pairs:
+        os.environ[k] = v
+      for c in [int(v) for v in os.environ.get("CANDS", "1,8,26").split(",")]:
+          W = np.random.default_rng(11 + c).normal(size=(c, d))
+          plan.eval_linear(W, per_query=False)
+          dev.profile(True)
+          dev.profile_read(reset=True)
+          for _ in range(reps):
+              sums, _ = plan.eval_linear(W, per_query=False)
+          launches, ms = dev.profile_read(reset=True)
+          dev.profile(False)
+          per_pass_ms = ms / reps
+          algo = n * d * 4 + n * 4 + (q + 1) * 4 + c * d * 8 + c * 8
+          print(json.dumps({
+              "setting": setting,
+              "workload": "full rescore, %d weight vectors per pass over %d x %d, ndcg@10" % (c, n, d),
+              "launches_per_pass": launches / reps, "ms_per_pass": per_pass_ms,
+              "evals_per_s": c / per_pass_ms * 1e3,
+              "algorithmic_bytes_per_pass": algo, "achieved_GBps": algo / per_pass_ms / 1e6,
+              "peak_GBps": peak, "frac": algo / per_pass_ms / 1e6 / peak,
+              "mean_ndcg10_first": float(sums[0]) * 2.0 ** -40 / nq,
+          }), flush=True)
+      for k, _ in pairs:
+        del os.environ[k]
     dev.close()
 
 
