@@ -20,8 +20,8 @@ def _mk(oracle, n, d, q, seed, shuffle=False):
 
 @pytest.mark.parametrize("shuffle,tma", [(False, False), (True, False), (False, True), (True, True)])
 def test_linear_batch_bit_exact(oracle, shuffle, tma, monkeypatch):
-    # tma: the same evaluation with X staged by TMA bulk copies (linear_tma_kernel, FASTRANK_TMA_EVAL=1;
-    # 11 vectors are served as one pass of 8 through the ring and one of 4)
+    # tma: the same evaluation with X staged by TMA bulk copies (linear_tma_kernel, FASTRANK_TMA_EVAL=1,
+    # which serves up to 8 vectors per pass: the 11 vectors go as 8 + 2 + 1)
     if tma:
         monkeypatch.setenv("FASTRANK_TMA_EVAL", "1")
     else:
@@ -35,7 +35,12 @@ def test_linear_batch_bit_exact(oracle, shuffle, tma, monkeypatch):
     try:
         for name, metric, depth in METRICS:
             plan = dev.plan(metric, depth)
-            sums, pq = plan.eval_linear(W)
+            if tma:
+                parts = [plan.eval_linear(W[a:b]) for a, b in ((0, 8), (8, 10), (10, 11))]
+                sums = np.concatenate([p[0] for p in parts])
+                pq = np.concatenate([p[1] for p in parts])
+            else:
+                sums, pq = plan.eval_linear(W)
             for c in range(W.shape[0]):
                 exp = oracle.evaluate_scores(ods, oracle.score_linear(X, W[c]), name)
                 assert np.array_equal(pq[c], exp), (name, c, np.abs(pq[c] - exp).max())
