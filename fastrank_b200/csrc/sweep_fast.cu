@@ -601,6 +601,10 @@ int launch_packed(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStr
     PlanView pv = pl->view();
     FastArgs args = a;
     args.n_split = gx / 4u;
+    if (const char *env = getenv("FASTRANK_NSPLIT_DIV")) {  // tuning knob: 0 = no quarter items
+        const int div = atoi(env);
+        args.n_split = div > 0 ? gx / (uint32_t)div : 0u;
+    }
     PackedView v;
     v.q_task_off = pl->fast.pk_q_task_off.p;
     v.q_order = pl->fast.pk_q_order.p;

@@ -19,6 +19,22 @@
 // Two barriers per tile instead of two per row group, ~0.55x the instructions.
 #pragma once
 
+// unroll factors of the two walk loops per chunk width (code size vs. latency hiding: at 4/4/4 the
+// kernel is ~75 KB of SASS and stalls on instruction fetch; measured 1.05 ms per bench step at
+// 4/4/4, 0.98 at 2/2/2, 0.97 at 2/4/4, 1.08 at 1/1/1)
+#ifndef PK_U16
+#define PK_U16 2
+#endif
+#ifndef PK_U8
+#define PK_U8 4
+#endif
+#ifndef PK_U4
+#define PK_U4 4
+#endif
+#ifndef PK_NO_W4
+#define PK_NO_W4 0
+#endif
+
 struct PackedView {
     const uint32_t *q_task_off;     // [nq_plan + 1] first task of a plan query
     const uint16_t *q_order;        // [nq_plan] tile-local query indices, costliest first
@@ -77,7 +93,8 @@ __device__ __forceinline__ void rank_chunk(const double2 *__restrict__ trow, dou
         cnt[i] = 0;
     }
     int jq = qs;
-#pragma unroll 4
+    constexpr int UNR = W == 16 ? PK_U16 : (W == 8 ? PK_U8 : PK_U4);
+#pragma unroll UNR
     for (; jq < t0; ++jq) {  // documents that win ties against the chunk's
         const double2 tx = trow[jq];
         const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
@@ -92,7 +109,7 @@ __device__ __forceinline__ void rank_chunk(const double2 *__restrict__ trow, dou
         }
     }
     jq = t0 + n;
-#pragma unroll 4
+#pragma unroll UNR
     for (; jq < qe; ++jq) {  // documents that lose ties
         const double2 tx = trow[jq];
         const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
@@ -277,7 +294,7 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
                 const unsigned long long tags = (unsigned long long)w.y | ((unsigned long long)w.z << 32);
                 if (n > 8)
                     rank_chunk<16>(trow, c, qs, qe, t0, n, tags, packed);
-                else if (n > 4)
+                else if (n > 4 || PK_NO_W4)
                     rank_chunk<8>(trow, c, qs, qe, t0, n, tags, packed);
                 else
                     rank_chunk<4>(trow, c, qs, qe, t0, n, tags, packed);
