@@ -872,6 +872,53 @@ int fr_dev_device_count(void) {
     return n;
 }
 
+// Host -> device copy of a large pageable array: kUploaders threads, each staging chunks through
+// its own pinned buffer (allocated once per process) on its own stream.  Falls back to one
+// pageable copy on `fallback_stream` when pinned memory cannot be had.
+static cudaError_t upload_rows_staged(int device, void *dst, const void *src, size_t bytes, cudaStream_t fallback_stream) {
+    constexpr int kUploaders = 4;
+    constexpr size_t kChunk = (size_t)16 << 20;
+    static std::mutex mu;
+    static unsigned char *stage[kUploaders] = {nullptr, nullptr, nullptr, nullptr};
+    static bool tried = false, have = false;
+    std::lock_guard<std::mutex> lock(mu);  // one staged upload at a time per process
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    if (bytes < 4 * kChunk) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, fallback_stream);
+    if (!tried) {
+        tried = true;
+        have = true;
+        for (int w = 0; w < kUploaders; ++w)
+            if (cudaHostAlloc((void **)&stage[w], kChunk, cudaHostAllocPortable) != cudaSuccess) {
+                have = false;
+                cudaGetLastError();
+                break;
+            }
+    }
+    if (!have) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, fallback_stream);
+    const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
+    cudaError_t status[kUploaders];
+    std::vector<std::thread> pool;
+    for (int w = 0; w < kUploaders; ++w) {
+        pool.emplace_back([&, w]() {
+            status[w] = cudaSetDevice(device);
+            cudaStream_t st = nullptr;
+            if (status[w] == cudaSuccess) status[w] = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+            for (size_t c = (size_t)w; c < n_chunks && status[w] == cudaSuccess; c += kUploaders) {
+                const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+                memcpy(stage[w], (const unsigned char *)src + off, len);
+                status[w] = cudaMemcpyAsync((unsigned char *)dst + off, stage[w], len, cudaMemcpyHostToDevice, st);
+                if (status[w] == cudaSuccess) status[w] = cudaStreamSynchronize(st);  // the buffer is reused
+            }
+            if (st) cudaStreamDestroy(st);
+        });
+    }
+    for (auto &t : pool) t.join();
+    for (int w = 0; w < kUploaders; ++w)
+        if (status[w] != cudaSuccess) return status[w];
+    return cudaSuccess;
+}
+
 int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const float *gains,
                           const uint32_t *query_index, uint32_t n_queries, fr_dev_dataset **out) {
     if (!out) return fail("fr_dev_dataset_create: out is NULL");
@@ -902,12 +949,11 @@ int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const 
     CU(staging.alloc(n * d));
     CU(ds->x.alloc(ds->ld * d));
     lap("alloc");
+    // A pageable cudaMemcpy runs at ~11 GB/s here (one driver thread staging through pinned
+    // memory); four threads staging 16 MB chunks through their own pinned buffers reach the
+    // bandwidth of the host's memory system instead.
     cudaError_t copy_status = cudaSuccess;
-    std::thread copier([&]() {
-        copy_status = cudaSetDevice(device);
-        if (copy_status == cudaSuccess)
-            copy_status = cudaMemcpyAsync(staging.p, x, sizeof(float) * n * d, cudaMemcpyHostToDevice, ds->stream);
-    });
+    std::thread copier([&]() { copy_status = upload_rows_staged(device, staging.p, x, sizeof(float) * n * d, ds->stream); });
     struct Joiner {
         std::thread &t;
         ~Joiner() {
@@ -935,46 +981,67 @@ int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const 
         std::vector<uint32_t> fill(ds->q_start);
         for (size_t i = 0; i < n; ++i) ds->inst_of_pos[fill[query_index[i]]++] = (uint32_t)i;
     }
-    for (uint32_t q = 0; q < n_queries; ++q) {
-        uint32_t *b = ds->inst_of_pos.data() + ds->q_start[q];
-        const uint32_t len = ds->q_len[q];
-        if (len <= 64) {  // typical lists: a stable insertion sort, no allocation
-            for (uint32_t i = 1; i < len; ++i) {
-                const uint32_t v = b[i];
-                const float g = gains[v];
-                uint32_t j = i;
-                while (j > 0 && gains[b[j - 1]] > g) {
-                    b[j] = b[j - 1];
-                    --j;
-                }
-                b[j] = v;
-            }
-        } else {
-            std::stable_sort(b, b + len, [&](uint32_t a, uint32_t c) { return gains[a] < gains[c]; });
-        }
-    }
     ds->pos_of_inst.resize(n);
     ds->gain_pos.resize(n);
     std::vector<double> gexp(n);
     {
-        // 2^gain - 1 with the host libm, as the oracle does; labels take a handful of distinct
-        // values, so a flat cache probed from the most recent entry beats a tree
-        std::vector<std::pair<uint32_t, double>> cache;
-        size_t last = 0;
-        for (size_t p = 0; p < n; ++p) {
-            const uint32_t inst = ds->inst_of_pos[p];
-            ds->pos_of_inst[inst] = (uint32_t)p;
-            const float g = gains[inst];
-            ds->gain_pos[p] = g;
-            uint32_t bits;
-            memcpy(&bits, &g, 4);
-            if (cache.empty() || cache[last].first != bits) {
-                size_t at = 0;
-                while (at < cache.size() && cache[at].first != bits) ++at;
-                if (at == cache.size()) cache.emplace_back(bits, std::pow(2.0, (double)g) - 1.0);
-                last = at;
+        // per query: stable sort by gain, then the per-position tables; queries are independent, so
+        // the range is cut into a few slices of about equal document counts, one thread each
+        auto work = [&](uint32_t q_begin, uint32_t q_end) {
+            // 2^gain - 1 with the host libm, as the oracle does; labels take a handful of distinct
+            // values, so a flat cache probed from the most recent entry beats a tree
+            std::vector<std::pair<uint32_t, double>> cache;
+            size_t last = 0;
+            for (uint32_t q = q_begin; q < q_end; ++q) {
+                uint32_t *b = ds->inst_of_pos.data() + ds->q_start[q];
+                const uint32_t len = ds->q_len[q];
+                if (len <= 64) {  // typical lists: a stable insertion sort, no allocation
+                    for (uint32_t i = 1; i < len; ++i) {
+                        const uint32_t v = b[i];
+                        const float g = gains[v];
+                        uint32_t j = i;
+                        while (j > 0 && gains[b[j - 1]] > g) {
+                            b[j] = b[j - 1];
+                            --j;
+                        }
+                        b[j] = v;
+                    }
+                } else {
+                    std::stable_sort(b, b + len, [&](uint32_t a, uint32_t c) { return gains[a] < gains[c]; });
+                }
+                for (size_t p = ds->q_start[q]; p < (size_t)ds->q_start[q] + len; ++p) {
+                    const uint32_t inst = ds->inst_of_pos[p];
+                    ds->pos_of_inst[inst] = (uint32_t)p;
+                    const float g = gains[inst];
+                    ds->gain_pos[p] = g;
+                    uint32_t bits;
+                    memcpy(&bits, &g, 4);
+                    if (cache.empty() || cache[last].first != bits) {
+                        size_t at = 0;
+                        while (at < cache.size() && cache[at].first != bits) ++at;
+                        if (at == cache.size()) cache.emplace_back(bits, std::pow(2.0, (double)g) - 1.0);
+                        last = at;
+                    }
+                    gexp[p] = cache[last].second;
+                }
             }
-            gexp[p] = cache[last].second;
+        };
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned n_workers = (unsigned)std::min<size_t>(std::min(hw, 8u), std::max<size_t>(1, n / 100000));
+        if (n_workers <= 1) {
+            work(0, n_queries);
+        } else {
+            std::vector<std::thread> pool;
+            uint32_t q_at = 0;
+            for (unsigned w = 0; w < n_workers; ++w) {
+                const size_t want = n * (w + 1) / n_workers;  // documents up to the end of this slice
+                uint32_t q_to = q_at;
+                while (q_to < n_queries && (size_t)ds->q_start[q_to] + ds->q_len[q_to] <= want) ++q_to;
+                if (w + 1 == n_workers) q_to = n_queries;
+                pool.emplace_back(work, q_at, q_to);
+                q_at = q_to;
+            }
+            for (auto &t : pool) t.join();
         }
     }
     cudaStream_t s = ds->stream;
@@ -1018,6 +1085,13 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
     if (desc->depth == 0) return fail("fr_dev_plan_create: depth 0 is not a usable cut-off");
     CU(cudaSetDevice(ds->device));
     std::unique_ptr<fr_dev_plan> pl(new fr_dev_plan());
+    const bool trace = getenv("FASTRANK_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (trace)
+            fprintf(stderr, "[fastrank_b200] plan_create    %-14s +%.1f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     pl->ds = ds;
     pl->metric = desc->metric;
     pl->depth = desc->depth < 0 || desc->depth > INT_MAX ? INT_MAX : (int)desc->depth;
@@ -1027,15 +1101,18 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
         CU(cudaGetDeviceProperties(&prop, ds->device));
         pl->sm_count = prop.multiProcessorCount;
     }
-    // 1. collect the positions of every view query
-    std::vector<std::vector<uint32_t>> qpos(desc->n_queries);
+    // 1. the positions of every view query: a whole query is the run [q_start, q_start + q_len) and
+    //    is not materialised; an instance subset (sampling.rs:67-72) is collected and sorted
+    std::vector<std::vector<uint32_t>> qpos(desc->inst_off ? desc->n_queries : 0);
+    std::vector<uint32_t> view_q(desc->n_queries);
     std::vector<uint32_t> long_views;
     uint32_t max_len = 0, longest = 0;
     for (uint32_t v = 0; v < desc->n_queries; ++v) {
         const uint32_t q = desc->query_ids ? desc->query_ids[v] : v;
         if (q >= ds->nq) return fail("fr_dev_plan_create: query id out of range");
-        std::vector<uint32_t> &pos = qpos[v];
+        view_q[v] = q;
         if (desc->inst_off) {
+            std::vector<uint32_t> &pos = qpos[v];
             for (uint64_t k = desc->inst_off[v]; k < desc->inst_off[v + 1]; ++k) {
                 const uint32_t inst = desc->inst_ids[k];
                 if (inst >= ds->n) return fail("fr_dev_plan_create: instance id out of range");
@@ -1046,11 +1123,11 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
             }
             std::sort(pos.begin(), pos.end());
             pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
-        } else {
-            pos.resize(ds->q_len[q]);
-            for (uint32_t k = 0; k < ds->q_len[q]; ++k) pos[k] = ds->q_start[q] + k;
         }
     }
+    const bool subset = desc->inst_off != nullptr;
+    auto qlen = [&](uint32_t v) -> uint32_t { return subset ? (uint32_t)qpos[v].size() : ds->q_len[view_q[v]]; };
+    auto qposition = [&](uint32_t v, uint32_t k) -> uint32_t { return subset ? qpos[v][k] : ds->q_start[view_q[v]] + k; };
     // Which lists are tiled.  Tiles hold whole queries; the batched sweep takes tiles of up to
     // kFastTile documents, the exact-order kernels up to kMaxTile.  A few long lists must not push
     // a whole dataset off the batched sweep, so when at most a quarter of the documents sit in
@@ -1059,9 +1136,10 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
     uint32_t tile_cap = (uint32_t)kMaxTile;
     {
         uint64_t docs = 0, docs_over = 0;
-        for (const auto &pos : qpos) {
-            docs += pos.size();
-            if (pos.size() > (size_t)kFastTile) docs_over += pos.size();
+        for (uint32_t v = 0; v < desc->n_queries; ++v) {
+            const uint32_t len = qlen(v);
+            docs += len;
+            if (len > (uint32_t)kFastTile) docs_over += len;
         }
         if (docs_over > 0 && docs_over * 4 <= docs) tile_cap = (uint32_t)kFastTile;
         if (const char *env = getenv("FASTRANK_TILE_CAP")) {  // test knob: 32 .. kMaxTile
@@ -1070,7 +1148,7 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
         }
     }
     for (uint32_t v = 0; v < desc->n_queries; ++v) {
-        const uint32_t len = (uint32_t)qpos[v].size();
+        const uint32_t len = qlen(v);
         if (len > tile_cap) {
             long_views.push_back(v);  // ranked from HBM by long_queries.cu
             longest = std::max(longest, len);
@@ -1079,6 +1157,7 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
         }
     }
     pl->max_len = max_len;
+    lap("positions");
     int tb = 128;
     if (const char *env = getenv("FASTRANK_TB")) tb = atoi(env) >= 256 ? 256 : 128;  // tuning knob
     while (tb < (int)max_len) tb *= 2;
@@ -1091,8 +1170,17 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
         tile_q_off.push_back((uint32_t)pq_local.size());
         cur_docs = 0;
     };
+    {
+        uint64_t docs = 0;
+        for (uint32_t v = 0; v < desc->n_queries; ++v) docs += qlen(v);
+        pd_pos.reserve(docs);
+        pd_q.reserve(docs);
+        pq_local.reserve(desc->n_queries);
+        pq_doc0.reserve(desc->n_queries);
+        pq_view.reserve(desc->n_queries);
+    }
     for (uint32_t v = 0; v < desc->n_queries; ++v) {
-        const uint32_t len = (uint32_t)qpos[v].size();
+        const uint32_t len = qlen(v);
         if (len > tile_cap) continue;
         if (cur_docs + len > (uint32_t)tb && cur_docs > 0) close_tile();
         const uint32_t start = cur_docs;
@@ -1100,7 +1188,7 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
         pq_doc0.push_back((uint32_t)pd_pos.size());
         pq_view.push_back(v);
         for (uint32_t k = 0; k < len; ++k) {
-            pd_pos.push_back(qpos[v][k]);
+            pd_pos.push_back(qposition(v, k));
             pd_q.push_back(start | ((start + len) << 16));
         }
         cur_docs += len;
@@ -1116,21 +1204,28 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
                 pl->contiguous = false;
                 break;
             }
+    lap("tiles");
     // 3. discount table with the host libm (evaluators.rs:269: log2(i + 2))
     std::vector<double> lg2(std::max<uint32_t>(std::max(max_len, longest), 1));
     for (size_t i = 0; i < lg2.size(); ++i) lg2[i] = std::log2((double)i + 2.0);
     cudaStream_t s = ds->stream;
-    CU(pl->lg2.upload(lg2, s));
-    CU(pl->tile_doc_off.upload(tile_doc_off, s));
-    CU(pl->tile_q_off.upload(tile_q_off, s));
-    CU(pl->pd_pos.upload(pd_pos, s));
-    CU(pl->pd_q.upload(pd_q, s));
-    CU(pl->pq_local.upload(pq_local, s));
-    CU(pl->pq_doc0.upload(pq_doc0, s));
-    CU(pl->pq_view.upload(pq_view, s));
+    {
+        UploadBatch up;
+        up.add(pl->lg2, lg2);
+        up.add(pl->tile_doc_off, tile_doc_off);
+        up.add(pl->tile_q_off, tile_q_off);
+        up.add(pl->pd_pos, pd_pos);
+        up.add(pl->pd_q, pd_q);
+        up.add(pl->pq_local, pq_local);
+        up.add(pl->pq_doc0, pq_doc0);
+        up.add(pl->pq_view, pq_view);
+        CU(up.commit(pl->arena, s));
+    }
+    lap("uploads");
     CU(pl->pq_norm.alloc(pl->nq_plan));
     CU(pl->err_dev.alloc(1));
     CU(pl->err_host.ensure(1));
+    lap("allocs");
     // 4. norms
     DevBuf<uint8_t> ovp;
     DevBuf<double> ovv;
@@ -1146,9 +1241,19 @@ int fr_dev_plan_create(fr_dev_dataset *ds, const fr_dev_plan_desc *desc, fr_dev_
         LAUNCHED();
         CU(cudaGetLastError());
     }
+    lap("norms");
     if (build_fast_plan(pl.get(), tile_q_off, pq_local, pq_doc0, pd_pos)) return 1;
+    lap("sweep plan");
+    if (!subset && !long_views.empty()) {  // only the untiled lists are materialised
+        qpos.resize(desc->n_queries);
+        for (uint32_t v : long_views) {
+            qpos[v].resize(qlen(v));
+            for (uint32_t k = 0; k < (uint32_t)qpos[v].size(); ++k) qpos[v][k] = ds->q_start[view_q[v]] + k;
+        }
+    }
     if (build_long_plan(pl.get(), qpos, long_views, desc)) return 1;
     CU(cudaStreamSynchronize(s));
+    lap("done");
     pl->nq_global = pl->nq_view;
     *out = pl.release();
     return 0;

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdint>
@@ -44,14 +45,22 @@ template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    bool owns = true;  // false: a slice of an UploadBatch arena
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p && owns) cudaFree(p);
         p = nullptr;
         n = 0;
+        owns = true;
+    }
+    void adopt(T *ptr, size_t count) {
+        release();
+        p = ptr;
+        n = count;
+        owns = false;
     }
     cudaError_t alloc(size_t count) {
         release();
@@ -64,6 +73,53 @@ struct DevBuf {
         return cudaMemcpyAsync(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, s);
     }
     cudaError_t ensure(size_t count) { return count <= n && p ? cudaSuccess : alloc(count); }
+};
+
+// Several host arrays -> ONE device allocation and one copy per array (a plan uploads a dozen
+// small arrays; a cudaMalloc apiece costs more than the copies).
+struct UploadBatch {
+    struct Item {
+        void **slot;
+        size_t *count_slot;
+        bool *owns_slot;
+        const void *src;
+        size_t bytes, count, offset;
+    };
+    std::vector<Item> items;
+    size_t total = 0;
+    template <typename T>
+    void add(DevBuf<T> &dst, const std::vector<T> &h) {
+        dst.release();
+        Item it;
+        it.slot = (void **)&dst.p;
+        it.count_slot = &dst.n;
+        it.owns_slot = &dst.owns;
+        it.src = h.data();
+        it.bytes = sizeof(T) * h.size();
+        it.count = h.size();
+        it.offset = total;
+        total += (it.bytes + 255) & ~(size_t)255;
+        items.push_back(it);
+    }
+    cudaError_t commit(DevBuf<unsigned char> &arena, cudaStream_t s) {
+        const bool trace = getenv("FASTRANK_TRACE") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
+        cudaError_t e = arena.alloc(total ? total : 1);
+        if (e != cudaSuccess) return e;
+        if (trace)
+            fprintf(stderr, "[fastrank_b200]   arena cudaMalloc(%zu) %.2f ms\n", total,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        for (const Item &it : items) {
+            *it.slot = arena.p + it.offset;
+            *it.count_slot = it.count;
+            *it.owns_slot = false;
+            if (it.bytes) {
+                e = cudaMemcpyAsync(arena.p + it.offset, it.src, it.bytes, cudaMemcpyHostToDevice, s);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        return cudaSuccess;
+    }
 };
 
 template <typename T>
@@ -313,6 +369,9 @@ struct LongPlan {
 
 struct fr_dev_plan {
     fr_dev_dataset *ds = nullptr;
+    // one allocation each behind the plan's read-only arrays; declared first so that they are
+    // destroyed last (the DevBufs below that point into them do not own their memory)
+    DevBuf<unsigned char> arena, fast_arena;
     FastPlan fast;
     LongPlan lng;
     int metric = 0;

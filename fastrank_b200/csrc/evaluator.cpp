@@ -57,18 +57,23 @@ Evaluator::Evaluator(const DatasetView &view, const Measure &measure, const QRel
     ParentDataset &parent = *view.parent;
     fr_dev_dataset *dev = parent.device();
     use_lock_ = std::unique_lock<std::recursive_mutex>(parent.use_mu);
-    const auto groups = view.instances_by_query();
     std::vector<uint64_t> inst_off{0};
     std::vector<uint32_t> inst_ids;
     bool subset = false;
-    for (const auto &g : groups) {
-        view_queries_.push_back(g.first);
-        if (g.second.size() != parent.by_query[g.first].size()) subset = true;
-    }
-    if (subset) {
+    if (!view.sampled) {  // every query of the parent, whole: nothing to group
+        view_queries_.resize(parent.by_query.size());
+        for (uint32_t q = 0; q < view_queries_.size(); ++q) view_queries_[q] = q;
+    } else {
+        const auto groups = view.instances_by_query();
         for (const auto &g : groups) {
-            inst_ids.insert(inst_ids.end(), g.second.begin(), g.second.end());
-            inst_off.push_back(inst_ids.size());
+            view_queries_.push_back(g.first);
+            if (g.second.size() != parent.by_query[g.first].size()) subset = true;
+        }
+        if (subset) {
+            for (const auto &g : groups) {
+                inst_ids.insert(inst_ids.end(), g.second.begin(), g.second.end());
+                inst_off.push_back(inst_ids.size());
+            }
         }
     }
     // a plan built earlier for the same view and measure (no judgments involved) is reused

@@ -669,6 +669,11 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
         }
     }
     cudaStream_t s = ds->stream;
+    UploadBatch up;  // every array of the sweep plan in one allocation
+    std::vector<double> tbl_host, tbl0;
+    std::vector<uint32_t> q_task_off{0}, pk_tile_off{0};
+    std::vector<uint4> pk_tasks;
+    std::vector<uint16_t> q_order;
     fp.n_cls = 0;
     fp.tbl_r = 1;
     if (table && !cls_gain.empty()) {
@@ -680,11 +685,12 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
         }
         fp.n_cls = (uint32_t)cls_gain.size();
         fp.tbl_r = R;
-        CU(fp.disc_tbl.upload(tbl, s));
+        tbl_host = tbl;
     } else {
         std::fill(pd_cls.begin(), pd_cls.end(), 0);
     }
-    CU(fp.pd_cls.upload(pd_cls, s));
+    if (!tbl_host.empty()) up.add(fp.disc_tbl, tbl_host);
+    up.add(fp.pd_cls, pd_cls);
     // warp tasks: runs of documents that can contribute, cut into chunks of td
     std::vector<uint32_t> tile_task_off{0};
     std::vector<uint2> tasks;
@@ -722,15 +728,13 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
         tile_task_off.push_back((uint32_t)tasks.size());
     }
     fp.n_tasks = (uint32_t)tasks.size();
-    CU(fp.tile_task_off.upload(tile_task_off, s));
-    CU(fp.tasks.upload(tasks, s));
+    up.add(fp.tile_task_off, tile_task_off);
+    up.add(fp.tasks, tasks);
     fp.ok = true;
     // sweep_packed_kernel: NDCG@k, k <= 16 ranks of 4 bits in one register per candidate
     fp.packed_ok = false;
     if (ndcg && fp.n_cls >= 1 && fp.n_cls <= 15 && pl->depth <= 16) {
-        std::vector<uint32_t> q_task_off{0}, pk_tile_off{0};
-        std::vector<uint4> pk_tasks;
-        std::vector<uint16_t> q_order(pq_local.size(), 0);
+        q_order.assign(pq_local.size(), 0);
         std::vector<std::pair<uint64_t, uint16_t>> cost;
         for (uint32_t tile = 0; tile + 1 < tile_q_off.size(); ++tile) {
             cost.clear();
@@ -769,18 +773,20 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
             pk_tile_off.push_back((uint32_t)pk_tasks.size());
         }
         // table with a leading row of zeros: tag 0 = nothing ranked there
-        std::vector<double> tbl0((size_t)(fp.n_cls + 1) * fp.tbl_r, 0.0);
+        tbl0.assign((size_t)(fp.n_cls + 1) * fp.tbl_r, 0.0);
         for (size_t c = 0; c < cls_gain.size(); ++c) {
             const double ge = std::pow(2.0, (double)cls_gain[c]) - 1.0;  // evaluators.rs:268
             for (uint32_t r = 0; r < fp.tbl_r; ++r) tbl0[(c + 1) * fp.tbl_r + r] = ge / std::log2((double)r + 2.0);
         }
-        CU(fp.pk_q_task_off.upload(q_task_off, s));
-        CU(fp.pk_tile_task_off.upload(pk_tile_off, s));
-        CU(fp.pk_tasks.upload(pk_tasks, s));
-        CU(fp.pk_q_order.upload(q_order, s));
-        CU(fp.pk_tbl.upload(tbl0, s));
+        up.add(fp.pk_q_task_off, q_task_off);
+        up.add(fp.pk_tile_task_off, pk_tile_off);
+        up.add(fp.pk_tasks, pk_tasks);
+        up.add(fp.pk_q_order, q_order);
+        up.add(fp.pk_tbl, tbl0);
         fp.packed_ok = true;
     }
+    CU(up.commit(pl->fast_arena, s));
+    CU(cudaStreamSynchronize(s));  // the host vectors above go out of scope
     return 0;
 }
 
