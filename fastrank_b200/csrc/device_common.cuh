@@ -348,7 +348,21 @@ struct FastPlan {
     // tile counters; each moves with a single copy through pinned memory
     DevBuf<unsigned char> in_dev, out_dev;
     PinnedBuf<unsigned char> in_host, out_host;
+    // direct publication (sweep_fast.cu, FastArgs::host_flag): device-side state that the kernel
+    // itself leaves zeroed, and a host-mapped block the last CTA writes sums / errors / a flag into
+    DevBuf<unsigned char> state_dev;
+    unsigned char *pub_host = nullptr;  // cudaHostAlloc(Mapped)
+    unsigned char *pub_dev = nullptr;   // the same block as the device sees it
+    uint32_t pub_epoch = 0;
+    bool direct_open = false;  // a direct call did not complete: the device state may not be zero
+    ~FastPlan() {
+        if (pub_host) cudaFreeHost(pub_host);
+    }
 };
+constexpr uint32_t kDirectGroups = 64;                       // tile counters in the direct state block
+constexpr size_t kDirectSumsOff = 512;                       // [err i32][done u32][tile ctr u32 x 64] ... [sums]
+constexpr size_t kDirectStateBytes = kDirectSumsOff + sizeof(long long) * 4096;
+constexpr size_t kPubErrOff = sizeof(long long) * 4096;      // [sums i64 x 4096][err i32][flag u32]
 
 struct FastView {
     const uint32_t *tile_task_off;

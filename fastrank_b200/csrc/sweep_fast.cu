@@ -65,6 +65,14 @@ struct FastArgs {
     unsigned *done_ctr;                // CTAs that have flushed their sums (zeroed before the launch)
     uint32_t mail_rank, mail_world, mail_epoch, mail_words;
     uint32_t n_split;  // tiles handed out as quarter items (the last ones of the queue)
+    // direct publication (nullptr: the host copies the sums back itself): the last CTA writes the
+    // final sums and error flags into host-mapped pinned memory, clears the device-side state for
+    // the next launch and raises host_flag = host_epoch, which the host spins on -- no memset, no
+    // device-to-host copy and no stream synchronisation per step
+    long long *host_sums;
+    int *host_err;
+    unsigned *host_flag;
+    uint32_t host_epoch;
 };
 
 // system-scope flag accesses for the peer mailboxes
@@ -113,36 +121,54 @@ __device__ __forceinline__ void fused_allreduce_tail(const FastArgs &A, int *s_m
     __syncthreads();
     if (!s_misc[M_TILE]) return;
     __threadfence();
-    const uint32_t world = A.mail_world, me = A.mail_rank, buf = A.mail_epoch & 1u, nw = A.mail_words;
-    const size_t slot = sizeof(long long) * kMailWords;
-    for (uint32_t r = 0; r < world; ++r) {
-        long long *dst = (long long *)(A.mail_peers[r] + ((size_t)buf * world + me) * slot);
-        for (uint32_t i = t; i < nw; i += TB) dst[i] = __ldcg(A.sums + i);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((uint32_t)t < world) {
-        unsigned *flag = (unsigned *)(A.mail_peers[t] + Mailbox::flags_offset((int)world)) + buf * world + me;
-        st_release_sys(flag, A.mail_epoch);
-        const unsigned *mine = (const unsigned *)(A.mail_peers[me] + Mailbox::flags_offset((int)world)) + buf * world + t;
-        const long long t_begin = clock64();
-        while (ld_acquire_sys(mine) != A.mail_epoch) {
-            if (clock64() - t_begin > 8000000000ll) {  // ~4 s: a peer never made this call
-                atomicOr(A.err, ERR_PEER_TIMEOUT);
-                break;
+    const uint32_t nw = A.mail_words;
+    if (A.mail_peers != nullptr) {
+        const uint32_t world = A.mail_world, me = A.mail_rank, buf = A.mail_epoch & 1u;
+        const size_t slot = sizeof(long long) * kMailWords;
+        for (uint32_t r = 0; r < world; ++r) {
+            long long *dst = (long long *)(A.mail_peers[r] + ((size_t)buf * world + me) * slot);
+            for (uint32_t i = t; i < nw; i += TB) dst[i] = __ldcg(A.sums + i);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((uint32_t)t < world) {
+            unsigned *flag = (unsigned *)(A.mail_peers[t] + Mailbox::flags_offset((int)world)) + buf * world + me;
+            st_release_sys(flag, A.mail_epoch);
+            const unsigned *mine = (const unsigned *)(A.mail_peers[me] + Mailbox::flags_offset((int)world)) + buf * world + t;
+            const long long t_begin = clock64();
+            while (ld_acquire_sys(mine) != A.mail_epoch) {
+                if (clock64() - t_begin > 8000000000ll) {  // ~4 s: a peer never made this call
+                    atomicOr(A.err, ERR_PEER_TIMEOUT);
+                    break;
+                }
+                __nanosleep(200);
             }
-            __nanosleep(200);
+        }
+        __syncthreads();
+        __threadfence_system();
+        const unsigned char *box = A.mail_peers[me] + (size_t)buf * world * slot;
+        for (uint32_t i = t; i < nw; i += TB) {
+            long long total = 0;
+            for (uint32_t r = 0; r < world; ++r)
+                total += *(const volatile long long *)(box + (size_t)r * slot + sizeof(long long) * i);
+            A.sums[i] = total;
         }
     }
+    if (A.host_flag == nullptr) return;
+    // publish to the host and leave the device-side state zeroed for the next launch
     __syncthreads();
-    __threadfence_system();
-    const unsigned char *box = A.mail_peers[me] + (size_t)buf * world * slot;
     for (uint32_t i = t; i < nw; i += TB) {
-        long long total = 0;
-        for (uint32_t r = 0; r < world; ++r)
-            total += *(const volatile long long *)(box + (size_t)r * slot + sizeof(long long) * i);
-        A.sums[i] = total;
+        A.host_sums[i] = *(volatile long long *)(A.sums + i);
+        A.sums[i] = 0;
     }
+    for (uint32_t g = t; g < gridDim.y; g += TB) A.tile_ctr[g] = 0u;
+    if (t == 0) {
+        *A.host_err = atomicExch(A.err, 0);
+        *A.done_ctr = 0u;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) st_release_sys(A.host_flag, A.host_epoch);
 }
 
 template <int TB>
@@ -517,7 +543,7 @@ sweep_fast_kernel(PlanView P, FastView F, FastArgs A) {
     __syncthreads();
     for (int idx = t; idx < R; idx += TB)
         atomicAdd((unsigned long long *)(A.sums + A.row_out[row0 + idx]), s_sum[idx]);
-    if (A.mail_peers == nullptr) return;
+    if (A.mail_peers == nullptr && A.host_flag == nullptr) return;
     fused_allreduce_tail<TB>(A, s_misc);
 }
 
@@ -835,13 +861,7 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
     const size_t out_bytes = sizeof(long long) * total + 8 + sizeof(unsigned) * (n_groups + 1);
     CU(fp.in_dev.ensure(in_bytes));
     CU(fp.in_host.ensure(in_bytes));
-    CU(fp.out_dev.ensure(out_bytes));
-    CU(fp.out_host.ensure(sizeof(long long) * total + 8));
     if (out_per_query) CU(pl->perq_dev.ensure(total * (size_t)pl->nq_view));
-    long long *sums_dev = (long long *)fp.out_dev.p;
-    int *err_dev = (int *)(fp.out_dev.p + sizeof(long long) * total);
-    unsigned *ctr_dev = (unsigned *)(fp.out_dev.p + sizeof(long long) * total + 8);
-    unsigned *done_dev = ctr_dev + n_groups;
     // passes needed (a sweep group holds kMaxRows candidate rows per pass); the cross-GPU
     // reduction is fused into the last one
     size_t n_passes = 1;
@@ -853,6 +873,45 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
     }
     fr_dev_comm *comm = pl->comm && pl->comm->world > 1 ? pl->comm : nullptr;
     const bool fuse = comm && comm->mail.ok && total <= kMailWords;
+    // Direct publication: the kernel's last CTA hands the sums to the host through mapped pinned
+    // memory and re-zeroes the device state, so a step is one small H2D copy and one launch.
+    bool direct = !out_per_query && total <= 4096 && n_groups <= kDirectGroups && n_passes == 1 && pl->nt > 0 &&
+                  (!comm || fuse);
+    if (const char *env = getenv("FASTRANK_DIRECT")) direct = direct && atoi(env) != 0;
+    if (direct && !fp.pub_host) {
+        if (cudaHostAlloc((void **)&fp.pub_host, kPubErrOff + 8, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+            cudaHostGetDevicePointer((void **)&fp.pub_dev, fp.pub_host, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (fp.pub_host) cudaFreeHost(fp.pub_host);
+            fp.pub_host = nullptr;
+            direct = false;
+        } else {
+            memset(fp.pub_host, 0, kPubErrOff + 8);
+            CU(fp.state_dev.alloc(kDirectStateBytes));
+            CU(cudaMemsetAsync(fp.state_dev.p, 0, kDirectStateBytes, s));
+        }
+    }
+    long long *sums_dev;
+    int *err_dev;
+    unsigned *ctr_dev, *done_dev;
+    if (direct) {
+        if (fp.direct_open) {  // an earlier call failed between launch and publication
+            CU(cudaStreamSynchronize(s));
+            CU(cudaMemsetAsync(fp.state_dev.p, 0, kDirectStateBytes, s));
+        }
+        fp.direct_open = true;
+        err_dev = (int *)fp.state_dev.p;
+        done_dev = (unsigned *)(fp.state_dev.p + 4);
+        ctr_dev = (unsigned *)(fp.state_dev.p + 8);
+        sums_dev = (long long *)(fp.state_dev.p + kDirectSumsOff);
+    } else {
+        CU(fp.out_dev.ensure(out_bytes));
+        CU(fp.out_host.ensure(sizeof(long long) * total + 8));
+        sums_dev = (long long *)fp.out_dev.p;
+        err_dev = (int *)(fp.out_dev.p + sizeof(long long) * total);
+        ctr_dev = (unsigned *)(fp.out_dev.p + sizeof(long long) * total + 8);
+        done_dev = ctr_dev + n_groups;
+    }
     // NDCG@k (k <= 16) takes the register-packed kernel; it tests for NaN scores only where T or
     // x_f is not finite, so candidates that are not finite themselves go to the general kernel
     bool use_packed = fp.packed_ok;
@@ -863,7 +922,7 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         if (std::string(env) == "tile") use_packed = false;
     }
     size_t pass = 0;
-    CU(cudaMemsetAsync(fp.out_dev.p, 0, out_bytes, s));
+    if (!direct) CU(cudaMemsetAsync(fp.out_dev.p, 0, out_bytes, s));
     if (out_per_query)
         CU(cudaMemsetAsync(pl->perq_dev.p, 0, sizeof(double) * total * (size_t)pl->nq_view, s));
     bool first_pass = true;
@@ -930,6 +989,10 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         a.mail_world = comm ? (uint32_t)comm->world : 1u;
         a.mail_epoch = fuse_now ? ++comm->mail.epoch : 0u;
         a.mail_words = (uint32_t)total;
+        a.host_sums = direct ? (long long *)fp.pub_dev : nullptr;
+        a.host_err = direct ? (int *)(fp.pub_dev + kPubErrOff) : nullptr;
+        a.host_flag = direct ? (unsigned *)(fp.pub_dev + kPubErrOff + 4) : nullptr;
+        a.host_epoch = direct ? ++fp.pub_epoch : 0u;
         // lists that do not fit a tile are scored from the same staged tables and ranked from HBM
         // (long_queries.cu); their sums land in sums_dev BEFORE the tile kernel runs, so the fused
         // cross-GPU reduction in its tail covers them as well
@@ -978,6 +1041,30 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
                             : launch_fast<512, 4, false>(pl, a, n_groups, s);
         }
         if (rc) return 1;
+    }
+    if (direct) {
+        // spin on the flag the last CTA raises (a stream query now and then catches a failed launch)
+        volatile unsigned *flag = (volatile unsigned *)(fp.pub_host + kPubErrOff + 4);
+        const unsigned want = fp.pub_epoch;
+        for (unsigned spins = 0; *flag != want; ++spins) {
+            if ((spins & 0xfff) == 0xfff) {
+                const cudaError_t q = cudaStreamQuery(s);
+                if (q != cudaErrorNotReady) {
+                    if (q != cudaSuccess) return fail(std::string("sweep kernel failed: ") + cudaGetErrorString(q));
+                    if (*flag != want) return fail("sweep kernel finished without publishing its sums");
+                }
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        fp.direct_open = false;
+        int err_flags;
+        memcpy(&err_flags, fp.pub_host + kPubErrOff, sizeof(int));
+        if (check_err_flags(err_flags)) return 1;
+        memcpy(out_sum_fx, fp.pub_host, sizeof(long long) * total);
+        return 0;
     }
     if (!fuse && allreduce_sums(pl, sums_dev, total, s)) return 1;
     CU(cudaMemcpyAsync(fp.out_host.p, fp.out_dev.p, sizeof(long long) * total + 8, cudaMemcpyDeviceToHost, s));

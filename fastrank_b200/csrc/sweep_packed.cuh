@@ -326,6 +326,6 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
     __syncthreads();
     for (int idx = t; idx < R; idx += TB)
         atomicAdd((unsigned long long *)(A.sums + A.row_out[row0 + idx]), s_sum[idx]);
-    if (A.mail_peers == nullptr) return;
+    if (A.mail_peers == nullptr && A.host_flag == nullptr) return;
     fused_allreduce_tail<TB>(A, s_misc);
 }
