@@ -341,6 +341,34 @@ class CDataset(_Handle):
     def predict_scores(self, model: CModel) -> Dict[int, float]:
         return model.predict_scores(self)
 
+    def bootstrap_eval(self, model: CModel, evaluator: str, qrel: Optional[CQRel] = None,
+                       num_trials: int = 200) -> Dict[str, float]:
+        """SetEvaluator::bootstrap_eval + PercentileStats::summary (evaluators.rs:157-171,
+        stats.rs:139-165): the per-query values of `model` are resampled with replacement
+        `num_trials` times (Rand64::new(0xdeadbeef), as the reference does); returns the mean and
+        the 5/25/50/75/95th percentiles of the resampled means, plus the sorted means."""
+        self._require_init()
+        model._require_init()
+        qrel_pointer = ffi.NULL if qrel is None else qrel.pointer
+        means = np.empty(num_trials, dtype=np.float64)
+        _check_fast_path(lib.evaluate_bootstrap_f64(model.pointer, self.pointer, qrel_pointer,
+                                                   evaluator.encode("utf-8"), num_trials,
+                                                   ffi.cast("double*", means.ctypes.data)))
+
+        def percentile(p: float) -> float:  # stats.rs:142-156, weights as the reference has them
+            n = p * (len(means) - 1)
+            lhs = int(n)
+            rhs = min(len(means), int(np.ceil(n)))
+            interp = n - int(n)
+            if lhs == rhs:
+                return float(means[lhs])
+            return float(interp * means[lhs] + (1.0 - interp) * means[rhs])
+
+        out = {"mean": self.evaluate_mean(model, evaluator, qrel), "means": means}
+        for name, p in (("p5", 0.05), ("p25", 0.25), ("p50", 0.5), ("p75", 0.75), ("p95", 0.95)):
+            out[name] = percentile(p)
+        return out
+
     def device_profile(self, enable: Optional[bool] = None, read: bool = False):
         """Per-kernel device timing of this dataset's scoring / ranking launches (CUDA events on
         the library's stream).  enable=True/False switches it; read=True returns

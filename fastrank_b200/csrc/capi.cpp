@@ -423,6 +423,28 @@ const void *evaluate_mean_f64(const CModel *model, const CDataset *dataset, cons
     }
 }
 
+const void *evaluate_bootstrap_f64(const CModel *model, const CDataset *dataset, const CQRel *qrel,
+                                   const void *evaluator, uint32_t num_trials, double *out_means) {
+    try {
+        const CModel &m = need(model);
+        const CDataset &d = need(dataset);
+        if (!out_means) throw Error("NULL pointer: out_means");
+        const Measure measure = Measure::parse(accept_str("evaluator_name", evaluator));
+        Evaluator ev(d.view, measure, qrel ? qrel->qrel.get() : nullptr);
+        std::vector<double> per_query;
+        ev.evaluate_mean(m.model, &per_query, m.uid);  // evaluate_to_vec, evaluators.rs:158
+        if (per_query.empty()) throw Error("bootstrap_eval: the view has no queries");
+        if (fr_dev_plan_bootstrap(ev.plan(), per_query.data(), per_query.size(), 0xdeadbeefull, num_trials, out_means))
+            throw Error(fr_dev_last_error());
+        for (uint32_t t = 0; t < num_trials; ++t)
+            if (out_means[t] != out_means[t]) throw Error("PercentileStats::NaN");  // stats.rs:134
+        std::sort(out_means, out_means + num_trials);  // stats.rs:136
+        return nullptr;
+    } catch (const std::exception &e) {
+        return dup_cstr(error_json(e.what()));
+    }
+}
+
 const void *dataset_device_profile(const CDataset *dataset, int enable, uint64_t *out_launches,
                                    double *out_total_ms) {
     try {

@@ -336,7 +336,11 @@ DatasetView load_ranksvm(const std::string &path, const std::string *feature_nam
             for (uint32_t f = 0; f <= max_feature; ++f) feature_set.insert(f);
         } else {
             len = 0;  // sparse instance
-            for (const auto &fv : row.feats) feature_set.insert(fv.first);
+            std::vector<uint32_t> &ids = ds->sparse_ids[(uint32_t)rows.size()];
+            for (const auto &fv : row.feats) {
+                feature_set.insert(fv.first);
+                ids.push_back(fv.first);
+            }
         }
         ds->row_len.push_back(len);
         ds->gains.push_back(label);
@@ -354,6 +358,10 @@ DatasetView load_ranksvm(const std::string &path, const std::string *feature_nam
     ds->n = rows.size();
     ds->features.assign(feature_set.begin(), feature_set.end());
     ds->d = (size_t)ds->features.back() + 1;
+    // the device layout is dense (instance.rs keeps Sparse32 rows; the kernels stream a matrix)
+    if (ds->n * ds->d > ((size_t)1 << 36))
+        throw Error(path + ": " + std::to_string(ds->n) + " x " + std::to_string(ds->d) +
+                    " values do not fit the dense device layout of this build");
     ds->owned_x.assign(ds->n * ds->d, 0.0f);
     for (size_t i = 0; i < ds->n; ++i)
         for (const auto &fv : rows[i].feats) ds->owned_x[i * ds->d + fv.first] = fv.second;

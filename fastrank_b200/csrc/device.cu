@@ -575,6 +575,37 @@ __global__ void __launch_bounds__(TB) scores_eval_kernel(PlanView P, const doubl
     if (t == 0) atomicAdd((unsigned long long *)sums, s_sum[0]);
 }
 
+// evaluators.rs:157-171 on the device: thread = trial.  oorandom::Rand64 (=11.1.0) is a 128-bit
+// LCG with a 64-bit output function; the reference draws trials * n indices from ONE stream, so
+// trial t starts n * t steps into it (the host computes those states by LCG jump-ahead) -- valid
+// as long as no draw is rejected by Lemire's test (probability ~n / 2^64 per draw; a rejection
+// raises *rejected and the host redoes the resampling sequentially).
+__global__ void bootstrap_kernel(const double *__restrict__ values, uint64_t n, uint32_t trials,
+                                 const uint64_t *__restrict__ start_states, uint64_t inc_lo, uint64_t inc_hi,
+                                 double *__restrict__ out_means, int *rejected) {
+    typedef unsigned __int128 u128;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= trials) return;
+    const u128 mult = (((u128)0x2360ED051FC65DA4ull) << 64) | (u128)0x4385DF649FCCF645ull;
+    const u128 inc = (((u128)inc_hi) << 64) | (u128)inc_lo;
+    u128 state = (((u128)start_states[2 * t + 1]) << 64) | (u128)start_states[2 * t];
+    const uint64_t threshold = (0 - n) % n;
+    double sum = 0.0;
+    bool bad = false;
+    for (uint64_t k = 0; k < n; ++k) {
+        const u128 old = state;
+        state = old * mult + inc;
+        const unsigned rot = (unsigned)(old >> 122);
+        const uint64_t xsh = (uint64_t)(((old >> 29) ^ old) >> 58);
+        const uint64_t u = (xsh >> rot) | (xsh << ((64 - rot) & 63));
+        const uint64_t lo = u * n, hi = __umul64hi(u, n);
+        bad |= lo < n && lo < threshold;
+        sum = __dadd_rn(sum, values[hi]);
+    }
+    out_means[t] = sum / (double)n;
+    if (bad) atomicOr(rejected, 1);
+}
+
 // ModelEnum interpreter: one thread per document position (model.rs:18-112).
 __global__ void model_score_kernel(const float *__restrict__ x, size_t ld, uint32_t dfeat, size_t n,
                                    const uint64_t *__restrict__ code,
@@ -1491,6 +1522,85 @@ int fr_dev_eval_model(fr_dev_plan *pl, const fr_dev_model *m, int64_t *out_sum_f
     return 0;
 }
 
+int fr_dev_plan_bootstrap(fr_dev_plan *pl, const double *values, size_t n_values, uint64_t seed, uint32_t trials,
+                          double *out_means) {
+    if (!pl || !values || !out_means) return fail("fr_dev_plan_bootstrap: NULL argument");
+    if (n_values == 0) return fail("fr_dev_plan_bootstrap: no values to resample (the reference divides by zero here)");
+    if (pl->comm && pl->comm->world > 1) return fail("fr_dev_plan_bootstrap: not available for a query-sharded plan");
+    if (trials == 0) return 0;
+    typedef unsigned __int128 u128;
+    const u128 mult = (((u128)0x2360ED051FC65DA4ull) << 64) | (u128)0x4385DF649FCCF645ull;
+    const u128 dflt = (((u128)0x2FE0E169FFBD06E3ull) << 64) | (u128)0x5BC307BD4D2F814Full;
+    const u128 inc = (dflt << 1) | 1;
+    // Rand64::new(seed): state 0, step, add the seed, step
+    u128 state = (u128)0 * mult + inc;
+    state += (u128)seed;
+    state = state * mult + inc;
+    // n steps at once: state -> A * state + C with (A, C) = (mult, inc) composed n times
+    u128 A = 1, C = 0, a = mult, c = inc;
+    for (uint64_t k = (uint64_t)n_values; k; k >>= 1) {
+        if (k & 1) {
+            A = A * a;
+            C = C * a + c;
+        }
+        c = c * a + c;
+        a = a * a;
+    }
+    std::vector<uint64_t> starts(2 * (size_t)trials);
+    for (uint32_t t = 0; t < trials; ++t) {
+        starts[2 * t] = (uint64_t)state;
+        starts[2 * t + 1] = (uint64_t)(state >> 64);
+        state = state * A + C;
+    }
+    fr_dev_dataset *ds = pl->ds;
+    CU(cudaSetDevice(ds->device));
+    cudaStream_t s = ds->stream;
+    DevBuf<double> vals, means;
+    DevBuf<uint64_t> st;
+    DevBuf<int> rej;
+    CU(vals.alloc(n_values));
+    CU(means.alloc(trials));
+    CU(st.alloc(starts.size()));
+    CU(rej.alloc(1));
+    CU(cudaMemcpyAsync(vals.p, values, sizeof(double) * n_values, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(st.p, starts.data(), sizeof(uint64_t) * starts.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(rej.p, 0, sizeof(int), s));
+    bootstrap_kernel<<<(trials + 31) / 32, 32, 0, s>>>(vals.p, (uint64_t)n_values, trials, st.p, (uint64_t)inc,
+                                                      (uint64_t)(inc >> 64), means.p, rej.p);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    int rejected = 0;
+    CU(cudaMemcpyAsync(out_means, means.p, sizeof(double) * trials, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&rejected, rej.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (rejected) {
+        // a draw was rejected somewhere: the stream positions above are off from there on, so the
+        // resampling is redone in order (same arithmetic, one thread)
+        const uint64_t n = (uint64_t)n_values, threshold = (0 - n) % n;
+        u128 stt = (u128)0 * mult + inc;
+        stt += (u128)seed;
+        stt = stt * mult + inc;
+        auto next = [&]() {
+            const u128 old = stt;
+            stt = old * mult + inc;
+            const unsigned rot = (unsigned)(old >> 122);
+            const uint64_t xsh = (uint64_t)(((old >> 29) ^ old) >> 58);
+            return (xsh >> rot) | (xsh << ((64 - rot) & 63));
+        };
+        for (uint32_t t = 0; t < trials; ++t) {
+            double sum = 0.0;
+            for (uint64_t k = 0; k < n; ++k) {
+                u128 m = (u128)next() * (u128)n;
+                if ((uint64_t)m < n)
+                    while ((uint64_t)m < threshold) m = (u128)next() * (u128)n;
+                sum += values[(uint64_t)(m >> 64)];
+            }
+            out_means[t] = sum / (double)n;
+        }
+    }
+    return 0;
+}
+
 int fr_dev_timer_start(fr_dev_dataset *ds) {
     if (!ds) return fail("fr_dev_timer_start: NULL dataset");
     CU(cudaSetDevice(ds->device));
@@ -1551,6 +1661,10 @@ int fr_dev_comm_create(int device, int rank, int world, const uint8_t id[128], f
     if (!api.ok) return fail(api.why);
     CU(cudaSetDevice(device));
     std::unique_ptr<fr_dev_comm> c(new fr_dev_comm());
+    {
+        static std::atomic<uint64_t> next_generation{1};
+        c->generation = next_generation.fetch_add(1);
+    }
     c->device = device;
     c->rank = rank;
     c->world = world;
@@ -1606,6 +1720,8 @@ int fr_dev_comm_create(int device, int rank, int world, const uint8_t id[128], f
     *out = c.release();
     return 0;
 }
+
+uint64_t fr_dev_comm_generation(const fr_dev_comm *comm) { return comm ? comm->generation : 0; }
 
 void fr_dev_comm_destroy(fr_dev_comm *comm) {
     if (!comm) return;

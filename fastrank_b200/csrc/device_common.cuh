@@ -234,6 +234,7 @@ struct Mailbox {
 };
 
 struct fr_dev_comm {
+    uint64_t generation = 0;  // unique per communicator ever created (a freed address can be reused)
     int device = 0;
     int rank = 0;
     int world = 1;

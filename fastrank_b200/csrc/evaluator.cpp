@@ -82,6 +82,7 @@ Evaluator::Evaluator(const DatasetView &view, const Measure &measure, const QRel
     if (cacheable) {
         for (const std::shared_ptr<PlanHolder> &h : parent.plan_cache) {
             if (h->metric == measure.metric && h->depth == measure.depth && h->comm == comm_now &&
+                h->comm_generation == fr_dev_comm_generation(comm_now) &&
                 h->sampled == view.sampled && (!view.sampled || h->instances == view.instances)) {
                 holder_ = h;
                 plan_ = h->plan;
@@ -128,6 +129,7 @@ Evaluator::Evaluator(const DatasetView &view, const Measure &measure, const QRel
         holder_->sampled = view.sampled;
         if (view.sampled) holder_->instances = view.instances;
         holder_->comm = comm_now;
+        holder_->comm_generation = fr_dev_comm_generation(comm_now);
         if (parent.plan_cache.size() >= 8) parent.plan_cache.erase(parent.plan_cache.begin());
         parent.plan_cache.push_back(holder_);
     }

@@ -112,6 +112,7 @@ struct PlanHolder {
     bool sampled = false;
     std::vector<uint32_t> instances;  // the view's instances when sampled
     fr_dev_comm *comm = nullptr;
+    uint64_t comm_generation = 0;  // fr_dev_comm_generation(comm) when the plan was built
     ~PlanHolder() {
         if (plan) fr_dev_plan_destroy(plan);
     }
@@ -129,7 +130,10 @@ struct ParentDataset {
     std::vector<std::vector<uint32_t>> by_query;
     std::vector<std::string> docids;           // empty when the dataset has none
     std::vector<uint8_t> has_docid;
-    std::vector<uint32_t> row_len;             // loaded data: features present up to this index
+    std::vector<uint32_t> row_len;             // loaded data: features present up to this index (0: sparse row)
+    // Sparse32 rows (instance.rs:104-122): the ids the row lists, ascending -- Some(0.0) and
+    // None stay distinct (normalizers.rs:21-27 skips only what the row does not carry)
+    std::unordered_map<uint32_t, std::vector<uint32_t>> sparse_ids;
     std::vector<uint32_t> features;            // ascending ids of the features present
     std::map<uint32_t, std::string> feature_names;
     bool dense_source = false;

@@ -63,9 +63,14 @@ struct Ctx {
         const float v = ds.x[(size_t)inst * ds.d + fid];
         if (!ds.dense_source) {
             const uint32_t len = ds.row_len[inst];
-            // dense row: ids below its length are present; sparse row (len 0): the listed ones,
-            // which the densified matrix can only tell apart from absent ones when non-zero
-            if (len > 0 ? fid >= len : v == 0.0f) return false;
+            // dense row: ids below its length are present; sparse row (len 0): the listed ones
+            if (len > 0) {
+                if (fid >= len) return false;
+            } else {
+                auto it = ds.sparse_ids.find(inst);
+                if (it == ds.sparse_ids.end() || !std::binary_search(it->second.begin(), it->second.end(), fid))
+                    return false;
+            }
         }
         *out = (double)v;
         return true;

@@ -64,6 +64,7 @@ struct FastArgs {
     unsigned char *const *mail_peers;  // [world] every rank's mailbox, own included
     unsigned *done_ctr;                // CTAs that have flushed their sums (zeroed before the launch)
     uint32_t mail_rank, mail_world, mail_epoch, mail_words;
+    long long mail_timeout_cycles;     // how long the last CTA waits for its peers (FASTRANK_PEER_TIMEOUT_S, default 30 s)
     uint32_t n_split;  // tiles handed out as quarter items (the last ones of the queue)
     // direct publication (nullptr: the host copies the sums back itself): the last CTA writes the
     // final sums and error flags into host-mapped pinned memory, clears the device-side state for
@@ -137,7 +138,7 @@ __device__ __forceinline__ void fused_allreduce_tail(const FastArgs &A, int *s_m
             const unsigned *mine = (const unsigned *)(A.mail_peers[me] + Mailbox::flags_offset((int)world)) + buf * world + t;
             const long long t_begin = clock64();
             while (ld_acquire_sys(mine) != A.mail_epoch) {
-                if (clock64() - t_begin > 8000000000ll) {  // ~4 s: a peer never made this call
+                if (clock64() - t_begin > A.mail_timeout_cycles) {  // a peer never made this call
                     atomicOr(A.err, ERR_PEER_TIMEOUT);
                     break;
                 }
@@ -989,6 +990,14 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         a.mail_world = comm ? (uint32_t)comm->world : 1u;
         a.mail_epoch = fuse_now ? ++comm->mail.epoch : 0u;
         a.mail_words = (uint32_t)total;
+        {
+            static const long long timeout_cycles = [] {
+                double sec = 30.0;  // rank skew (a slow stdout, a debugger, preemption) is not an error
+                if (const char *env = getenv("FASTRANK_PEER_TIMEOUT_S")) sec = std::max(0.001, atof(env));
+                return (long long)(sec * 2.0e9);
+            }();
+            a.mail_timeout_cycles = timeout_cycles;
+        }
         a.host_sums = direct ? (long long *)fp.pub_dev : nullptr;
         a.host_err = direct ? (int *)(fp.pub_dev + kPubErrOff) : nullptr;
         a.host_flag = direct ? (unsigned *)(fp.pub_dev + kPubErrOff + 4) : nullptr;

@@ -97,6 +97,15 @@ const void *predict_dense_f64(const CModel *model, const CDataset *dataset, doub
 const void *evaluate_mean_f64(const CModel *model, const CDataset *dataset, const CQRel *qrel,
                               const void *evaluator, double *out_mean);
 
+/* evaluators.rs:157-171 (SetEvaluator::bootstrap_eval; the reference calls it from
+ * print_standard_eval with 200 trials): the model is evaluated per query, the per-query values are
+ * resampled with replacement `num_trials` times with Rand64::new(0xdeadbeef), and out_means
+ * receives the resampled means SORTED ascending (what PercentileStats::new holds, stats.rs:131-138).
+ * Queries are taken in view order (the reference iterates a HashMap, so its own result varies from
+ * run to run).  Returns NULL on success, else an error JSON string (free_str). */
+const void *evaluate_bootstrap_f64(const CModel *model, const CDataset *dataset, const CQRel *qrel,
+                                   const void *evaluator, uint32_t num_trials, double *out_means);
+
 /* Device-side timing for reports (bench.py): brackets every scoring / ranking kernel this
  * dataset launches with CUDA events on the library's stream (fr_dev_profile_* below, reached
  * through the reference-facing handle).  enable: 1 on, 0 off, -1 leave as is; when out_launches /
@@ -215,6 +224,15 @@ int fr_dev_plan_has_fast_sweep(const fr_dev_plan *plan);
  * has no batched sweep.  For reports (bench.py roofline.kernel). */
 const char *fr_dev_plan_sweep_kernel(const fr_dev_plan *plan);
 
+/* Bootstrap resampling of per-query values (evaluators.rs:157-171): `trials` means of n_values
+ * draws with replacement from `values` (the per-query output of an evaluation, view order),
+ * drawn with oorandom::Rand64::new(seed).rand_range(0..n) exactly as the reference does -- one
+ * sequential stream across all trials, one sequential f64 sum per trial.  On the device each
+ * trial is one thread started at its position in the stream (128-bit LCG jump-ahead); out_means
+ * receives the means in trial order.  Single-GPU plans only. */
+int fr_dev_plan_bootstrap(fr_dev_plan *plan, const double *values, size_t n_values, uint64_t seed,
+                          uint32_t trials, double *out_means);
+
 /* Flattened ModelEnum (model.rs:10-16).  `code` is a postfix program of 64-bit words; see
  * fastrank_b200/csrc/model_program.hpp for the encoding produced by the host. */
 int fr_dev_model_create(fr_dev_dataset *ds, const uint64_t *code, size_t n_words,
@@ -268,6 +286,9 @@ int fr_dev_rf_partition(fr_dev_rf *rf, uint32_t n_active, const uint32_t *fid, c
 int fr_dev_comm_unique_id(uint8_t out_id[128]);
 int fr_dev_comm_create(int device, int rank, int world, const uint8_t id[128], fr_dev_comm **out);
 void fr_dev_comm_destroy(fr_dev_comm *comm);
+/* A number unique to this communicator for the life of the process (0 for NULL): what caches
+ * keyed on a communicator compare, since a destroyed communicator's address can be reused. */
+uint64_t fr_dev_comm_generation(const fr_dev_comm *comm);
 /* Sum-all-reduce of n uint64 words held in host memory (used for setup-time counts). */
 int fr_dev_comm_allreduce_u64(fr_dev_comm *comm, uint64_t *inout, size_t n);
 /* Process-wide default: plans created through the reference-compatible surface

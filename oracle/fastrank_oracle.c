@@ -110,6 +110,22 @@ uint64_t fro_rng_range(fro_rng *r, uint64_t start, uint64_t end) {
     return (uint64_t)(m >> 64);
 }
 
+/* evaluators.rs:157-171: SetEvaluator::bootstrap_eval -- `trials` means of n draws with
+ * replacement from the per-query values, one Rand64::new(0xdeadbeef) stream across all trials,
+ * a sequential f64 sum per trial. */
+void fro_bootstrap_means(const double *values, uint64_t n, uint32_t trials, double *out_means) {
+    fro_rng r;
+    fro_rng_seed(&r, 0xdeadbeefULL, 0);
+    for (uint32_t t = 0; t < trials; t++) {
+        double sum = 0.0;
+        for (uint64_t k = 0; k < n; k++) {
+            uint64_t index = fro_rng_range(&r, 0, n);
+            sum = sum + values[index];
+        }
+        out_means[t] = sum / (double)n;
+    }
+}
+
 /* randutil.rs:21-27 */
 static void fro_shuffle_u32(uint32_t *v, size_t n, fro_rng *r) {
     for (size_t i = 0; i < n; i++) {

