@@ -356,6 +356,15 @@ struct FastPlan {
     unsigned char *pub_dev = nullptr;   // the same block as the device sees it
     uint32_t pub_epoch = 0;
     bool direct_open = false;  // a direct call did not complete: the device state may not be zero
+    std::vector<uint32_t> len_docs;  // len_docs[l] = tiled documents sitting in lists of exactly l documents
+    double long_list_docs_frac(uint32_t min_len) const {
+        uint64_t all = 0, lng = 0;
+        for (size_t l = 0; l < len_docs.size(); ++l) {
+            all += len_docs[l];
+            if (l >= min_len) lng += len_docs[l];
+        }
+        return all ? (double)lng / (double)all : 0.0;
+    }
     ~FastPlan() {
         if (pub_host) cudaFreeHost(pub_host);
     }

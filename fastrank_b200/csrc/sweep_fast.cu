@@ -64,6 +64,7 @@ struct FastArgs {
     unsigned char *const *mail_peers;  // [world] every rank's mailbox, own included
     unsigned *done_ctr;                // CTAs that have flushed their sums (zeroed before the launch)
     uint32_t mail_rank, mail_world, mail_epoch, mail_words;
+    uint32_t prune_min;  // sweep_packed_kernel: lists of at least this many documents are pruned before ranking (0: never)
     long long mail_timeout_cycles;     // how long the last CTA waits for its peers (FASTRANK_PEER_TIMEOUT_S, default 30 s)
     uint32_t n_split;  // tiles handed out as quarter items (the last ones of the queue)
     // direct publication (nullptr: the host copies the sums back itself): the last CTA writes the
@@ -600,11 +601,11 @@ int launch_fast(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStrea
 
 #include "sweep_packed.cuh"
 
-template <int TB, bool WS, int MINB>
+template <int TB, bool WS, int MINB, int PS>
 int launch_packed(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStream_t stream) {
     const uint32_t dm8 = (a.dm + 7) & ~7u;
-    const PackedLayout L(TB, WS ? dm8 * kMaxSweeps : 0u);
-    auto kernel = sweep_packed_kernel<TB, WS, MINB>;
+    const PackedLayout L(TB, WS ? dm8 * kMaxSweeps : 0u, PS);
+    auto kernel = sweep_packed_kernel<TB, WS, MINB, PS>;
     static std::mutex mu;
     static std::map<std::pair<int, size_t>, int> cache;
     int occ = 0;
@@ -637,6 +638,7 @@ int launch_packed(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStr
     v.q_order = pl->fast.pk_q_order.p;
     v.tile_task_off = pl->fast.pk_tile_task_off.p;
     v.tasks = pl->fast.pk_tasks.p;
+    v.pd_cls = pl->fast.pd_cls.p;
     v.tbl = pl->fast.pk_tbl.p;
     v.tbl_r = pl->fast.tbl_r;
     v.n_cls = pl->fast.n_cls;
@@ -760,6 +762,8 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
     fp.ok = true;
     // sweep_packed_kernel: NDCG@k, k <= 16 ranks of 4 bits in one register per candidate
     fp.packed_ok = false;
+    fp.len_docs.assign((size_t)pl->tb + 1, 0);
+    for (uint32_t pq = 0; pq < pq_local.size(); ++pq) fp.len_docs[pq_local[pq] >> 16] += pq_local[pq] >> 16;
     if (ndcg && fp.n_cls >= 1 && fp.n_cls <= 15 && pl->depth <= 16) {
         q_order.assign(pq_local.size(), 0);
         std::vector<std::pair<uint64_t, uint16_t>> cost;
@@ -990,6 +994,8 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         a.mail_world = comm ? (uint32_t)comm->world : 1u;
         a.mail_epoch = fuse_now ? ++comm->mail.epoch : 0u;
         a.mail_words = (uint32_t)total;
+        a.prune_min = 48;
+        if (const char *env = getenv("FASTRANK_PRUNE_MIN")) a.prune_min = (uint32_t)std::max(0, atoi(env));
         {
             static const long long timeout_cycles = [] {
                 double sec = 30.0;  // rank skew (a slow stdout, a debugger, preemption) is not an error
@@ -1015,26 +1021,29 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         if (const char *env = getenv("FASTRANK_WSMEM")) ws = atoi(env) != 0;
         int rc;
         if (use_packed) {
+            // select-then-rank (sweep_packed.cuh) only where lists are long enough to pay for it
+            const bool prune = a.prune_min > 0 && fp.long_list_docs_frac(a.prune_min) >= 0.10;
             // resident CTAs per SM at 128 threads: 4 (<= 128 registers), 5 (<= 96) or 6 (<= 80)
-            int minb = 5;
+            int minb = prune ? 4 : 5;
             if (const char *env = getenv("FASTRANK_PACKED_MINB")) minb = atoi(env);
-            const size_t pk_bytes = PackedLayout(pl->tb, ((a.dm + 7) & ~7u) * kMaxSweeps).total;
-            const size_t room = pl->tb == 128 ? (size_t)(226 * 1024) / (size_t)std::max(4, std::min(minb, 6)) - 1024
-                                              : (size_t)100 * 1024;
+            minb = std::max(4, std::min(minb, 6));
+            const size_t pk_bytes = PackedLayout(pl->tb, ((a.dm + 7) & ~7u) * kMaxSweeps, prune ? kPruneSlots : 0).total;
+            const size_t room = pl->tb == 128 ? (size_t)(226 * 1024) / (size_t)minb - 1024
+                                              : (pl->tb == 256 ? (size_t)110 * 1024 : (size_t)220 * 1024);
             bool wsp = pk_bytes <= room;
             if (const char *env = getenv("FASTRANK_WSMEM")) wsp = atoi(env) != 0;
-            if (pl->tb == 128) {
-                if (minb <= 4)
-                    rc = wsp ? launch_packed<128, true, 4>(pl, a, n_groups, s) : launch_packed<128, false, 4>(pl, a, n_groups, s);
-                else if (minb == 5)
-                    rc = wsp ? launch_packed<128, true, 5>(pl, a, n_groups, s) : launch_packed<128, false, 5>(pl, a, n_groups, s);
-                else
-                    rc = wsp ? launch_packed<128, true, 6>(pl, a, n_groups, s) : launch_packed<128, false, 6>(pl, a, n_groups, s);
-            } else if (pl->tb == 256) {
-                rc = wsp ? launch_packed<256, true, 2>(pl, a, n_groups, s) : launch_packed<256, false, 2>(pl, a, n_groups, s);
-            } else {
-                rc = wsp ? launch_packed<512, true, 1>(pl, a, n_groups, s) : launch_packed<512, false, 1>(pl, a, n_groups, s);
-            }
+#define PK_LAUNCH(TB_, MINB_)                                                                                  \
+    (prune ? (wsp ? launch_packed<TB_, true, MINB_, kPruneSlots>(pl, a, n_groups, s)                           \
+                  : launch_packed<TB_, false, MINB_, kPruneSlots>(pl, a, n_groups, s))                         \
+           : (wsp ? launch_packed<TB_, true, MINB_, 0>(pl, a, n_groups, s)                                     \
+                  : launch_packed<TB_, false, MINB_, 0>(pl, a, n_groups, s)))
+            if (pl->tb == 128)
+                rc = minb <= 4 ? PK_LAUNCH(128, 4) : (minb == 5 ? PK_LAUNCH(128, 5) : PK_LAUNCH(128, 6));
+            else if (pl->tb == 256)
+                rc = PK_LAUNCH(256, 2);
+            else
+                rc = PK_LAUNCH(512, 1);
+#undef PK_LAUNCH
         } else if (pl->tb == 128) {
             if (ws)
                 rc = fp.td == 8 ? launch_fast<128, 8, true>(pl, a, n_groups, s)

@@ -41,15 +41,19 @@ struct PackedView {
     const uint32_t *tile_task_off;  // [nt + 1]
     const uint4 *tasks;             // .x = t0 | n << 16 (tile-local documents of one query, n <= 16),
                                     // .y/.z = their tags (gain class + 1), 4 bits each, 0 beyond n
+    const uint8_t *pd_cls;          // plan doc -> gain class (select-then-rank path)
     const double *tbl;              // [n_cls + 1][tbl_r]: row 0 zeros (empty slot), row c + 1 = class c
     uint32_t tbl_r, n_cls;
 };
 
+constexpr int kPruneSlots = 64;  // survivors a candidate may keep in the select-then-rank path
+
 struct PackedLayout {
-    size_t t2, sum, roww, tbl, qd, tasks, order, rowsw, misc, w, total;
-    __host__ __device__ PackedLayout(int tb, uint32_t w_doubles) {
+    size_t t2, sum, roww, tbl, qd, tasks, order, rowsw, misc, cls, surv, w, total;
+    // ps: survivor slots per candidate (0: the kernel instance has no select-then-rank path)
+    __host__ __device__ PackedLayout(int tb, uint32_t w_doubles, int ps) {
         size_t o = 0;
-        t2 = o;     o += sizeof(double2) * kMaxSweeps * (size_t)tb;
+        t2 = o;     o += sizeof(double2) * kMaxSweeps * (size_t)(tb + (ps > 0 ? 1 : 0));  // + one "never ranks" slot per row
         sum = o;    o += sizeof(unsigned long long) * kMaxRows;
         roww = o;   o += sizeof(double) * kMaxRows;
         tbl = o;    o += sizeof(double) * 16 * 16;
@@ -58,6 +62,8 @@ struct PackedLayout {
         order = o;  o += align16(sizeof(uint16_t) * tb);
         rowsw = o;  o += kMaxRows;
         misc = o;   o += 256;
+        cls = o;    o += align16((size_t)tb + 1);
+        surv = o;   o += (tb < 256 ? 1 : 2) * (size_t)(ps ? ps + 1 : 0) * 32 * (size_t)(tb / 32);  // [warp][slot][lane], + a scratch slot
         w = o;      o += sizeof(double) * w_doubles;
         total = o;
     }
@@ -120,7 +126,151 @@ __device__ __forceinline__ void rank_chunk(const double2 *__restrict__ trow, dou
     for (int i = 0; i < W; ++i) packed |= tag_at_rank((unsigned)(tags >> (4 * i)) & 15u, cnt[i]);
 }
 
-template <int TB, bool WS, int MINB>
+// Select-then-rank for long lists (NDCG@k, k << len).  Per candidate (lane):
+//   A. the list is cut into `lim` runs; thr = the smallest of the runs' maxima.  `lim` documents
+//      score >= thr, so a document below thr is outranked by at least `lim` others: it cannot be
+//      in the top `lim`, and it outranks nobody who is.
+//   B. the documents with score >= thr -- the survivors, in list order, which is the tie-break
+//      order -- are written to a lane-private list of PS indices; the rest of the list is padded
+//      with the tile's dummy slot (score -inf under every candidate, tag 0).
+//   B2. when some lane kept many, the same cut is applied to the survivor lists themselves (runs
+//      of list slots; a lane whose list is short gets thr = -inf and keeps everything).
+//   C. survivors are ranked among themselves by counting, 8 list slots at a time; a survivor's
+//      rank among survivors IS its rank in the whole list (everything that outranks a survivor is a
+//      survivor), so what lands in ranks < lim is exactly what the full count would put there.
+// Returns false (warp-uniform) when some lane has more survivors than slots; the caller then
+// takes the full count.
+template <int TB>
+struct SurvIndex {
+    typedef uint16_t type;
+};
+template <>
+struct SurvIndex<128> {
+    typedef uint8_t type;  // tile-local indices 0..128 fit a byte
+};
+
+template <int TB, int PS>
+__device__ __forceinline__ bool rank_pruned(const double2 *__restrict__ trow, double c, int qs, int qe, unsigned lim,
+                                            const uint8_t *__restrict__ s_cls,
+                                            typename SurvIndex<TB>::type *__restrict__ surv, int lane,
+                                            unsigned long long &packed) {
+    typedef typename SurvIndex<TB>::type surv_t;
+    const double kNegInf = __longlong_as_double(0xfff0000000000000ll);
+    const int len = qe - qs;
+    const int csize = len / (int)lim;
+    // A: two runs at a time (independent maxima: the chains of compares overlap)
+    double thr = __longlong_as_double(0x7ff0000000000000ll);
+    {
+        unsigned ch = 0;
+        for (; ch + 2 <= lim; ch += 2) {
+            const int ja = qs + (int)ch * csize, jb = ja + csize;
+            const int nb = ch + 2 == lim ? qe - jb : csize;  // the last run takes the remainder
+            double ma = kNegInf, mb = kNegInf;
+#pragma unroll 4
+            for (int u = 0; u < csize; ++u) {
+                const double2 ta = trow[ja + u], tb = trow[jb + u];
+                const double sa = __dadd_rn(ta.x, __dmul_rn(ta.y, c)), sb = __dadd_rn(tb.x, __dmul_rn(tb.y, c));
+                ma = sa > ma ? sa : ma;
+                mb = sb > mb ? sb : mb;
+            }
+            for (int u = csize; u < nb; ++u) {
+                const double2 tb = trow[jb + u];
+                const double sb = __dadd_rn(tb.x, __dmul_rn(tb.y, c));
+                mb = sb > mb ? sb : mb;
+            }
+            const double m2 = ma < mb ? ma : mb;
+            thr = m2 < thr ? m2 : thr;
+        }
+        if (ch < lim) {  // odd lim: the last run alone, with the remainder
+            double mx = kNegInf;
+            for (int j = qs + (int)ch * csize; j < qe; ++j) {
+                const double2 tx = trow[j];
+                const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+                mx = sj > mx ? sj : mx;
+            }
+            thr = mx < thr ? mx : thr;
+        }
+    }
+    // B: branch-free append (a document below thr writes the lane's scratch slot PS)
+    surv_t *mine = surv + lane;  // [slot][lane], PS + 1 slots
+    unsigned n_s = 0;
+#pragma unroll 4
+    for (int j = qs; j < qe; ++j) {
+        const double2 tx = trow[j];
+        const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+        const bool keep = sj >= thr;
+        const unsigned slot = keep ? (n_s < (unsigned)PS ? n_s : (unsigned)PS) : (unsigned)PS;
+        mine[slot * 32] = (surv_t)j;
+        n_s += keep ? 1u : 0u;
+    }
+    if (__any_sync(0xffffffffu, n_s > (unsigned)PS)) return false;
+    int n_max = (int)__reduce_max_sync(0xffffffffu, n_s);
+    for (int k = (int)n_s; k < ((n_max + 7) & ~7) && k < PS; ++k) mine[k * 32] = (surv_t)TB;  // padding: never ranks
+    // B2
+    if (n_max > 24 && n_max >= 2 * (int)lim) {
+        const int cs = (n_max + (int)lim - 1) / (int)lim;
+        double thr2 = __longlong_as_double(0x7ff0000000000000ll);
+        int k = 0;
+        for (unsigned ch = 0; ch < lim; ++ch) {
+            double mx = kNegInf;
+            for (int e = min(n_max, k + cs); k < e; ++k) {
+                const double2 tx = trow[mine[k * 32]];
+                const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+                mx = sj > mx ? sj : mx;
+            }
+            thr2 = mx < thr2 ? mx : thr2;
+        }
+        unsigned w = 0;
+#pragma unroll 2
+        for (k = 0; k < n_max; ++k) {
+            const unsigned id = mine[k * 32];
+            const double2 tx = trow[id];
+            const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+            const bool keep = id != (unsigned)TB && sj >= thr2;
+            mine[(keep ? w : (unsigned)PS) * 32] = (surv_t)id;  // w <= k: in place; the rest goes to the scratch slot
+            w += keep ? 1u : 0u;
+        }
+        const int n_new = (int)__reduce_max_sync(0xffffffffu, w);
+        for (k = (int)w; k < ((n_new + 7) & ~7) && k < PS; ++k) mine[k * 32] = (surv_t)TB;
+        n_max = n_new;
+    }
+    // C
+    for (int k1 = 0; k1 < n_max; k1 += 8) {
+        double st[8];
+        unsigned cnt[8], id[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            id[i] = k1 + i < PS ? mine[(k1 + i) * 32] : (unsigned)TB;
+            const double2 tx = trow[id[i]];
+            st[i] = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+            cnt[i] = 0;
+        }
+#pragma unroll 4
+        for (int k2 = 0; k2 < k1; ++k2) {  // earlier in list order: they win ties
+            const double2 tx = trow[mine[k2 * 32]];
+            const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) count_ge(cnt[i], sj, st[i]);
+        }
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+#pragma unroll
+            for (int i = 0; i < j; ++i) count_pair(cnt[i], cnt[j], st[i], st[j]);
+        }
+#pragma unroll 4
+        for (int k2 = k1 + 8; k2 < n_max; ++k2) {  // later in list order: they lose ties
+            const double2 tx = trow[mine[k2 * 32]];
+            const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) count_gt(cnt[i], sj, st[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) packed |= tag_at_rank(((unsigned)s_cls[id[i]] + 1u) & 15u, cnt[i]);
+    }
+    return true;
+}
+
+template <int TB, bool WS, int MINB, int PS>
 __global__ void __launch_bounds__(TB, MINB)
 sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -133,8 +283,12 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
     const int R = (int)(A.grp_row_off[blockIdx.y + 1] - row0);  // rows of this sweep group
     const int G = (R + 31) >> 5;
     const uint32_t dm8 = (dm + 7) & ~7u;
-    const PackedLayout L(TB, WS ? dm8 * NS : 0u);
-    double2 *s_t2 = (double2 *)(smem_raw + L.t2);  // [NS][TB]
+    const PackedLayout L(TB, WS ? dm8 * NS : 0u, PS);
+    double2 *s_t2 = (double2 *)(smem_raw + L.t2);  // [NS][TB + 1]
+    constexpr int T2S = PS > 0 ? TB + 1 : TB;     // slot TB of every row: a document that never ranks
+    uint8_t *s_cls = (uint8_t *)(smem_raw + L.cls);
+    typedef typename SurvIndex<TB>::type surv_t;
+    surv_t *s_surv = (surv_t *)(smem_raw + L.surv) + (size_t)(t >> 5) * (PS + 1) * 32;
     unsigned long long *s_sum = (unsigned long long *)(smem_raw + L.sum);
     double *s_roww = (double *)(smem_raw + L.roww);
     double *s_tbl = (double *)(smem_raw + L.tbl);
@@ -154,6 +308,10 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
         s_sum[idx] = 0ull;
     }
     for (uint32_t idx = t; idx < (V.n_cls + 1) * tbl_r; idx += TB) s_tbl[idx] = V.tbl[idx];
+    if (PS > 0) {
+        if (t < NS) s_t2[(size_t)t * T2S + TB] = make_double2(__longlong_as_double(0xfff0000000000000ll), 0.0);
+        if (t == 0) s_cls[TB] = (uint8_t)255;  // tag (255 + 1) & 15 = 0: files nothing
+    }
     if (WS)
         for (uint32_t idx = t; idx < dm8 * NS; idx += TB) s_w[idx] = wg[idx];
     __syncthreads();
@@ -195,6 +353,7 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
         const uint32_t q0 = P.tile_q_off[tile];
         const int nqt = (int)(P.tile_q_off[tile + 1] - q0);
         if (t < ntask) s_tasks[t] = V.tasks[task0 + t];
+        if (PS > 0) s_cls[t] = active ? __ldg(V.pd_cls + doc0 + t) : (uint8_t)255;
         if (t < nqt) {
             const uint32_t tb0 = V.q_task_off[q0 + t], tb1 = V.q_task_off[q0 + t + 1];
             s_qd[t] = make_uint2(P.pq_local[q0 + t], (tb0 - task0) | ((tb1 - tb0) << 16));
@@ -245,7 +404,7 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 odd |= !(fabs(acc[s]) <= 1.7976931348623157e308) || !(fabsf(xf[s]) <= 3.402823466e38f);
-                s_t2[(size_t)s * TB + t] = make_double2(active ? acc[s] : 0.0, active ? (double)xf[s] : 0.0);
+                s_t2[(size_t)s * T2S + t] = make_double2(active ? acc[s] : 0.0, active ? (double)xf[s] : 0.0);
             }
             if (odd && active) {
                 for (int r = (g_begin << 5); r < min(R, g_end << 5); ++r) {
@@ -286,9 +445,13 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
             const bool live = row < R;
             const int rowc = live ? row : R - 1;
             const double c = s_roww[rowc];
-            const double2 *trow = s_t2 + (size_t)s_rowsw[rowc] * TB;
+            const double2 *trow = s_t2 + (size_t)s_rowsw[rowc] * T2S;
             unsigned long long packed = 0ull;
-            for (int tk = tk0; tk < tk0 + ntk; ++tk) {
+            bool ranked = false;
+            if (PS > 0 && A.prune_min > 0 && len >= (int)A.prune_min && ntk > 0)
+                ranked = rank_pruned<TB, (PS > 0 ? PS : 8)>(trow, c, qs, qe, lim, s_cls, s_surv, lane, packed);
+            if (!ranked) packed = 0ull;
+            for (int tk = tk0; tk < tk0 + (ranked ? 0 : ntk); ++tk) {
                 const uint4 w = s_tasks[tk];
                 const int t0 = (int)(w.x & 0xffffu), n = (int)(w.x >> 16);
                 const unsigned long long tags = (unsigned long long)w.y | ((unsigned long long)w.z << 32);

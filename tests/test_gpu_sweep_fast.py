@@ -406,14 +406,24 @@ def test_packed_kernel_equals_general_kernel_bit_for_bit(oracle, monkeypatch, de
     got = {}
     try:
         plan = dev.plan(0, depth)
-        for which in ("tile", None):
+        # FASTRANK_PRUNE_MIN: lists of at least that many documents take the packed kernel's
+        # select-then-rank path (default 48; 0 = never; 2 = nearly every list, which also drives
+        # lists with more than 32 survivors per candidate into the fall-back to the full count)
+        for which, prune in (("tile", None), (None, None), (None, "0"), (None, "2")):
             if which is None:
                 monkeypatch.delenv("FASTRANK_SWEEP_KERNEL", raising=False)
             else:
                 monkeypatch.setenv("FASTRANK_SWEEP_KERNEL", which)
-            got[which] = plan.coord_sweeps(base, fids, cands, fast=True, per_query=True)
-        assert np.array_equal(got["tile"][0], got[None][0])
-        assert np.array_equal(got["tile"][1], got[None][1])
+            if prune is None:
+                monkeypatch.delenv("FASTRANK_PRUNE_MIN", raising=False)
+            else:
+                monkeypatch.setenv("FASTRANK_PRUNE_MIN", prune)
+            got[(which, prune)] = plan.coord_sweeps(base, fids, cands, fast=True, per_query=True)
+        monkeypatch.delenv("FASTRANK_PRUNE_MIN", raising=False)
+        for key in ((None, None), (None, "0"), (None, "2")):
+            assert np.array_equal(got[("tile", None)][0], got[key][0]), key
+            assert np.array_equal(got[("tile", None)][1], got[key][1]), key
+        got = {"tile": got[("tile", None)], None: got[(None, None)]}
         # and against the oracle on a few candidates
         name = "ndcg@%d" % depth
         for r, k in ((0, 0), (3, 17), (7, 50)):
