@@ -67,6 +67,7 @@ struct FastArgs {
     uint32_t prune_min;  // sweep_packed_kernel: lists of at least this many documents are pruned before ranking (0: never)
     long long mail_timeout_cycles;     // how long the last CTA waits for its peers (FASTRANK_PEER_TIMEOUT_S, default 30 s)
     uint32_t n_split;  // tiles handed out as quarter items (the last ones of the queue)
+    uint32_t split_parts;  // sweep_packed_kernel: parts a split tile is cut into (2 or 4)
     // direct publication (nullptr: the host copies the sums back itself): the last CTA writes the
     // final sums and error flags into host-mapped pinned memory, clears the device-side state for
     // the next launch and raises host_flag = host_epoch, which the host spins on -- no memset, no
@@ -628,11 +629,18 @@ int launch_packed(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStr
     if (gx > pl->nt) gx = std::max<uint32_t>(pl->nt, 1);  // an empty shard still takes part in the reduction
     PlanView pv = pl->view();
     FastArgs args = a;
-    args.n_split = gx / 4u;
-    if (const char *env = getenv("FASTRANK_NSPLIT_DIV")) {  // tuning knob: 0 = no quarter items
+    // Work granularity.  A CTA's unit is a tile (phase 1, then ~13 row groups x its queries as warp
+    // items).  With many tiles per CTA the last gx / 4 tiles are handed out as quarters (ranges of row
+    // groups, phase 1 repeated -- it is ~17 % of a tile) so that the SMs drain together; with fewer
+    // than two tiles per CTA repeating phase 1 costs more than the shorter tail saves (measured on
+    // 125 k .. 1 M document shards: 0.175 / 0.297 / 0.527 / 0.976 ms).
+    args.split_parts = 4;
+    args.n_split = (uint64_t)pl->nt >= 2ull * gx ? gx / 4u : 0u;
+    if (const char *env = getenv("FASTRANK_NSPLIT_DIV")) {  // tuning knob: 0 = no split items, -1 = every tile
         const int div = atoi(env);
-        args.n_split = div > 0 ? gx / (uint32_t)div : 0u;
+        args.n_split = div > 0 ? gx / (uint32_t)div : (div < 0 ? pl->nt : 0u);
     }
+    if (const char *env = getenv("FASTRANK_SPLIT_PARTS")) args.split_parts = atoi(env) == 2 ? 2u : 4u;
     PackedView v;
     v.q_task_off = pl->fast.pk_q_task_off.p;
     v.q_order = pl->fast.pk_q_order.p;

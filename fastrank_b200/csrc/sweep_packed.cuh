@@ -330,19 +330,20 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
 
     // Work items: whole tiles first; the last n_split tiles are handed out as quarter items (a
     // quarter of the row groups each, phase 1 repeated) so that the SMs drain together.
-    const uint32_t n_split = G >= 4 ? min(P.nt, A.n_split) : 0u;
+    const uint32_t parts = A.split_parts;  // 2 or 4 row-group ranges per split tile
+    const uint32_t n_split = (uint32_t)G >= parts ? min(P.nt, A.n_split) : 0u;
     const uint32_t n_whole = P.nt - n_split;
-    const uint32_t n_items = G > 0 ? n_whole + 4u * n_split : 0u;
+    const uint32_t n_items = G > 0 ? n_whole + parts * n_split : 0u;
     uint32_t next_item = n_items;
     for (uint32_t item = G > 0 ? (uint32_t)s_misc[M_TILE] : n_items; item < n_items; item = next_item) {
         if (t == 0) s_misc[M_NEXT] = (int)atomicAdd(A.tile_ctr + blockIdx.y, 1u);
         uint32_t tile = item;
         int g_begin = 0, g_end = G;
         if (item >= n_whole) {
-            const uint32_t j = item - n_whole, part = j & 3u;
-            tile = n_whole + (j >> 2);
-            g_begin = (int)((uint32_t)G * part / 4u);
-            g_end = (int)((uint32_t)G * (part + 1u) / 4u);
+            const uint32_t j = item - n_whole, part = j % parts;
+            tile = n_whole + j / parts;
+            g_begin = (int)((uint32_t)G * part / parts);
+            g_end = (int)((uint32_t)G * (part + 1u) / parts);
         }
         const uint32_t doc0 = P.tile_doc_off[tile];
         const int nd = (int)(P.tile_doc_off[tile + 1] - doc0);
