@@ -5,11 +5,14 @@
 // is shipped to the GPU once (ParentDataset::device) and never touched on the host again.
 #include <algorithm>
 #include <cerrno>
+#include <charconv>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <fstream>
 #include <set>
 #include <sstream>
+#include <thread>
 
 #include "host.hpp"
 
@@ -204,6 +207,17 @@ fr_dev_dataset *ParentDataset::device() {
         if (fr_dev_dataset_create(which, n, d, x, gains.data(), query_of.data(),
                                   (uint32_t)query_names.size(), &out))
             throw Error(std::string("GPU dataset upload failed: ") + fr_dev_last_error());
+        // libsvm data: which leading feature ids each (Dense32) row carries; Sparse32 rows are not
+        // described this way (random-forest statistics for such data stay on the host)
+        if (!dense_source && sparse_ids.empty() && row_len.size() == n) {
+            bool ragged = false;
+            for (uint32_t len : row_len) ragged |= len < d;
+            if (ragged && fr_dev_dataset_set_row_lengths(out, row_len.data())) {
+                const std::string why = fr_dev_last_error();
+                fr_dev_dataset_destroy(out);
+                throw Error("GPU dataset upload failed: " + why);
+            }
+        }
         dev = out;
     }
     return dev;
@@ -252,121 +266,237 @@ DatasetView load_ranksvm(const std::string &path, const std::string *feature_nam
             ds->feature_names[(uint32_t)id] = m.second.s;
         }
     }
-    std::istringstream in(read_file_by_extension(path));  // .gz / .bz2 / .zst by extension (io_helper.rs:18-29)
-
+    // The whole (decompressed, io_helper.rs:18-29) file is parsed from memory: it is cut at line
+    // boundaries into one slice per thread, every slice is parsed independently, and the slices are
+    // merged in file order, so instance ids, query order and the first error reported are those of
+    // a sequential read (libsvm.rs:205-260).
+    const bool trace = getenv("FASTRANK_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (trace)
+            fprintf(stderr, "[fastrank_b200] load_ranksvm   %-14s +%.1f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
+    const std::string text = read_file_by_extension(path);
+    lap("read");
     struct Row {
         std::vector<std::pair<uint32_t, float>> feats;
-    };
-    std::vector<Row> rows;
-    std::vector<std::string> qids;
-    std::set<uint32_t> feature_set;
-    std::string line;
-    size_t line_num = 0;
-    bool any_docid = false;
-    while (std::getline(in, line)) {
-        ++line_num;
-        auto bad = [&](const std::string &what) {
-            return Error(path + ": LineParseError(" + std::to_string(line_num) + ", " + what + ")");
-        };
-        std::string comment;
+        std::string qid, comment;
+        float label = 0.f;
         bool has_comment = false;
-        const size_t hash = line.find('#');
-        std::string data = line;
-        if (hash != std::string::npos) {
-            comment = line.substr(hash + 1);
-            const size_t b = comment.find_first_not_of(" \t\r\n");
-            const size_t e = comment.find_last_not_of(" \t\r\n");
-            comment = b == std::string::npos ? "" : comment.substr(b, e - b + 1);
-            has_comment = true;
-            data = line.substr(0, hash);
+    };
+    struct Slice {
+        size_t begin = 0, end = 0, first_line = 0;
+        std::vector<Row> rows;
+        bool failed = false;
+        std::string error;
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t n_slices = std::max<size_t>(1, std::min<size_t>(std::min(hw, 16u), text.size() / ((size_t)1 << 20)));
+    std::vector<Slice> slices(n_slices);
+    {
+        size_t at = 0;
+        for (size_t k = 0; k < n_slices; ++k) {
+            slices[k].begin = at;
+            size_t want = k + 1 == n_slices ? text.size() : text.size() * (k + 1) / n_slices;
+            if (want < at) want = at;
+            if (k + 1 < n_slices) {
+                const size_t nl = text.find('\n', want);
+                want = nl == std::string::npos ? text.size() : nl + 1;
+            }
+            slices[k].end = want;
+            at = want;
         }
-        std::istringstream ss(data);
-        std::vector<std::string> toks;
-        std::string tok;
-        while (ss >> tok) toks.push_back(tok);
-        if (toks.empty()) continue;
-        errno = 0;
-        char *endp = nullptr;
-        const double label64 = strtod(toks[0].c_str(), &endp);
-        if (endp != toks[0].c_str() + toks[0].size()) throw bad("Label(ParseFloatError { kind: Invalid })");
-        const float label = (float)label64;
-        if (label != label) throw bad("LabelIsNan(FloatIsNan)");
-        size_t k = 1;
-        std::string qid;
-        bool has_qid = false;
-        if (k < toks.size() && toks[k].compare(0, 4, "qid:") == 0) {
-            qid = toks[k];
-            while (qid.compare(0, 4, "qid:") == 0) qid = qid.substr(4);
-            has_qid = true;
-            ++k;
+        size_t line = 0;
+        for (size_t k = 0; k < n_slices; ++k) {
+            slices[k].first_line = line;
+            line += (size_t)std::count(text.begin() + (long)slices[k].begin, text.begin() + (long)slices[k].end, '\n');
         }
-        Row row;
-        for (; k < toks.size(); ++k) {
-            const size_t colon = toks[k].find(':');
-            if (colon == std::string::npos) throw bad("FeatureNoColon");
-            const std::string fs = toks[k].substr(0, colon), vs = toks[k].substr(colon + 1);
-            char *e1 = nullptr;
-            errno = 0;
-            const unsigned long long fid = strtoull(fs.c_str(), &e1, 10);
-            if (fs.empty() || *e1 != 0 || fs[0] == '-' || fs[0] == '+' || fid > 0xFFFFFFFFull || errno == ERANGE)
-                throw bad("FeatureNum(ParseIntError)");
-            bool ok = false;
-            const float val = parse_f32_strict(vs, &ok);
-            if (!ok) throw bad("FeatureValNotFloat(Error)");
-            row.feats.emplace_back((uint32_t)fid, val);
-        }
-        if (row.feats.empty()) throw bad("instance without features");
-        bool sorted = true;
-        for (size_t a = 0; a + 1 < row.feats.size(); ++a)
-            if (row.feats[a].first >= row.feats[a + 1].first) sorted = false;
-        if (!sorted) {
-            std::stable_sort(row.feats.begin(), row.feats.end(),
-                             [](const auto &l, const auto &r) { return l.first < r.first; });
+    }
+    auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; };
+    auto parse_slice = [&](Slice &sl) {
+        size_t line_num = sl.first_line;
+        const char *base = text.data();
+        size_t pos = sl.begin;
+        std::vector<std::pair<const char *, const char *>> toks;
+        std::string scratch;
+        while (pos < sl.end) {
+            size_t eol = text.find('\n', pos);
+            if (eol == std::string::npos || eol > sl.end) eol = sl.end;
+            const char *lb = base + pos, *le = base + eol;
+            pos = eol + 1;
+            ++line_num;
+            auto bad = [&](const std::string &what) {
+                sl.failed = true;
+                sl.error = path + ": LineParseError(" + std::to_string(line_num) + ", " + what + ")";
+            };
+            Row row;
+            const char *hash = (const char *)memchr(lb, '#', (size_t)(le - lb));
+            const char *de = le;
+            if (hash) {
+                const char *cb = hash + 1, *ce = le;
+                while (cb < ce && is_space(*cb)) ++cb;
+                while (ce > cb && is_space(ce[-1])) --ce;
+                row.comment.assign(cb, ce);
+                row.has_comment = true;
+                de = hash;
+            }
+            toks.clear();
+            for (const char *c = lb; c < de;) {
+                while (c < de && is_space(*c)) ++c;
+                if (c >= de) break;
+                const char *t0 = c;
+                while (c < de && !is_space(*c)) ++c;
+                toks.emplace_back(t0, c);
+            }
+            if (toks.empty()) continue;
+            auto cstr = [&](const char *b, const char *e) -> const char * {
+                scratch.assign(b, e);
+                return scratch.c_str();
+            };
+            {
+                const char *z = cstr(toks[0].first, toks[0].second);
+                char *endp = nullptr;
+                const double label64 = strtod(z, &endp);
+                if (endp != z + scratch.size()) return bad("Label(ParseFloatError { kind: Invalid })");
+                row.label = (float)label64;
+                if (row.label != row.label) return bad("LabelIsNan(FloatIsNan)");
+            }
+            size_t k = 1;
+            bool has_qid = false;
+            if (k < toks.size() && toks[k].second - toks[k].first >= 4 && memcmp(toks[k].first, "qid:", 4) == 0) {
+                const char *qb = toks[k].first;
+                while (toks[k].second - qb >= 4 && memcmp(qb, "qid:", 4) == 0) qb += 4;
+                row.qid.assign(qb, toks[k].second);
+                has_qid = true;
+                ++k;
+            }
+            row.feats.reserve(toks.size() - k);
+            for (; k < toks.size(); ++k) {
+                const char *tb = toks[k].first, *te = toks[k].second;
+                const char *colon = (const char *)memchr(tb, ':', (size_t)(te - tb));
+                if (!colon) return bad("FeatureNoColon");
+                unsigned long long fid = 0;
+                bool fid_ok = colon > tb;
+                for (const char *c = tb; c < colon && fid_ok; ++c) {
+                    if (*c < '0' || *c > '9') fid_ok = false;
+                    else fid = fid * 10 + (unsigned)(*c - '0');
+                    if (fid > 0xFFFFFFFFull) fid_ok = false;
+                }
+                if (!fid_ok) return bad("FeatureNum(ParseIntError)");
+                // plain decimals go through from_chars (correctly rounded, like the reference's
+                // fast-float); whatever it does not take whole ("+1", "inf", hex ...) is strtof's call
+                float val = 0.f;
+                const auto fc = std::from_chars(colon + 1, te, val);
+                if (fc.ec != std::errc() || fc.ptr != te) {
+                    const char *z = cstr(colon + 1, te);
+                    char *endp = nullptr;
+                    val = strtof(z, &endp);
+                    if (scratch.empty() || endp != z + scratch.size()) return bad("FeatureValNotFloat(Error)");
+                }
+                row.feats.emplace_back((uint32_t)fid, val);
+            }
+            if (row.feats.empty()) return bad("instance without features");
+            bool sorted = true;
             for (size_t a = 0; a + 1 < row.feats.size(); ++a)
-                if (row.feats[a].first == row.feats[a + 1].first) throw bad("MultipleDefinitions");
+                if (row.feats[a].first >= row.feats[a + 1].first) sorted = false;
+            if (!sorted) {
+                std::stable_sort(row.feats.begin(), row.feats.end(),
+                                 [](const auto &l, const auto &r) { return l.first < r.first; });
+                for (size_t a = 0; a + 1 < row.feats.size(); ++a)
+                    if (row.feats[a].first == row.feats[a + 1].first) return bad("MultipleDefinitions");
+            }
+            if (!has_qid) {
+                sl.failed = true;
+                sl.error = path + ": Missing qid";
+                return;
+            }
+            sl.rows.push_back(std::move(row));
         }
-        if (!has_qid) throw Error(path + ": Missing qid");
+    };
+    if (n_slices == 1) {
+        parse_slice(slices[0]);
+    } else {
+        std::vector<std::thread> pool;
+        for (size_t k = 0; k < n_slices; ++k) pool.emplace_back([&, k]() { parse_slice(slices[k]); });
+        for (auto &t : pool) t.join();
+    }
+    for (const Slice &sl : slices)  // the first error in file order, as a sequential reader would hit it
+        if (sl.failed) throw Error(sl.error);
+    lap("parsed");
+
+    size_t n_rows = 0;
+    for (const Slice &sl : slices) n_rows += sl.rows.size();
+    if (n_rows == 0) throw Error(path + ": No features defined!");
+    std::vector<const Row *> rows;
+    rows.reserve(n_rows);
+    for (const Slice &sl : slices)
+        for (const Row &r : sl.rows) rows.push_back(&r);
+    std::vector<std::string> qids(n_rows);
+    std::set<uint32_t> feature_set;
+    bool any_docid = false, any_dense = false;
+    uint32_t dense_max = 0;
+    ds->row_len.resize(n_rows);
+    ds->gains.resize(n_rows);
+    ds->docids.resize(n_rows);
+    ds->has_docid.resize(n_rows);
+    for (size_t i = 0; i < n_rows; ++i) {
+        const Row &row = *rows[i];
         // instance.rs:106-122: density >= 0.5 -> dense array of max_feature + 1 entries
         // (feature ids 0..=max become "present"), else only the listed ids are present
         const uint32_t max_feature = row.feats.back().first;
         const double density = (double)row.feats.size() / (double)max_feature;
-        uint32_t len;
         if (density >= 0.5) {
-            len = max_feature + 1;
-            for (uint32_t f = 0; f <= max_feature; ++f) feature_set.insert(f);
+            ds->row_len[i] = max_feature + 1;
+            dense_max = any_dense ? std::max(dense_max, max_feature) : max_feature;
+            any_dense = true;
         } else {
-            len = 0;  // sparse instance
-            std::vector<uint32_t> &ids = ds->sparse_ids[(uint32_t)rows.size()];
+            ds->row_len[i] = 0;  // sparse instance
+            std::vector<uint32_t> &ids = ds->sparse_ids[(uint32_t)i];
             for (const auto &fv : row.feats) {
                 feature_set.insert(fv.first);
                 ids.push_back(fv.first);
             }
         }
-        ds->row_len.push_back(len);
-        ds->gains.push_back(label);
-        qids.push_back(qid);
-        ds->docids.push_back(comment);
-        ds->has_docid.push_back(has_comment ? 1 : 0);
-        any_docid |= has_comment;
-        rows.push_back(std::move(row));
+        ds->gains[i] = row.label;
+        qids[i] = row.qid;
+        ds->docids[i] = row.comment;
+        ds->has_docid[i] = row.has_comment ? 1 : 0;
+        any_docid |= row.has_comment;
     }
-    if (rows.empty()) throw Error(path + ": No features defined!");
+    if (any_dense)
+        for (uint32_t f = 0; f <= dense_max; ++f) feature_set.insert(f);
     if (!any_docid) {
         ds->docids.clear();
         ds->has_docid.clear();
     }
-    ds->n = rows.size();
+    ds->n = n_rows;
     ds->features.assign(feature_set.begin(), feature_set.end());
     ds->d = (size_t)ds->features.back() + 1;
     // the device layout is dense (instance.rs keeps Sparse32 rows; the kernels stream a matrix)
     if (ds->n * ds->d > ((size_t)1 << 36))
         throw Error(path + ": " + std::to_string(ds->n) + " x " + std::to_string(ds->d) +
                     " values do not fit the dense device layout of this build");
+    lap("merged");
     ds->owned_x.assign(ds->n * ds->d, 0.0f);
-    for (size_t i = 0; i < ds->n; ++i)
-        for (const auto &fv : rows[i].feats) ds->owned_x[i * ds->d + fv.first] = fv.second;
+    {
+        auto fill = [&](size_t i0, size_t i1) {
+            for (size_t i = i0; i < i1; ++i)
+                for (const auto &fv : rows[i]->feats) ds->owned_x[i * ds->d + fv.first] = fv.second;
+        };
+        const size_t workers = n_rows >= 200000 ? std::min<size_t>(hw, 8) : 1;
+        if (workers <= 1) {
+            fill(0, n_rows);
+        } else {
+            std::vector<std::thread> pool;
+            for (size_t w = 0; w < workers; ++w) pool.emplace_back(fill, n_rows * w / workers, n_rows * (w + 1) / workers);
+            for (auto &t : pool) t.join();
+        }
+    }
     ds->x = ds->owned_x.data();
+    lap("densified");
     index_queries(*ds, qids);
+    lap("indexed");
     DatasetView view;
     view.parent = ds;
     return view;

@@ -1097,6 +1097,16 @@ int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const 
     return 0;
 }
 
+int fr_dev_dataset_set_row_lengths(fr_dev_dataset *ds, const uint32_t *row_len) {
+    if (!ds || !row_len) return fail("fr_dev_dataset_set_row_lengths: NULL argument");
+    CU(cudaSetDevice(ds->device));
+    std::vector<uint32_t> by_pos(ds->n);
+    for (size_t p = 0; p < ds->n; ++p) by_pos[p] = row_len[ds->inst_of_pos[p]];
+    CU(ds->len_pos.upload(by_pos, ds->stream));
+    CU(cudaStreamSynchronize(ds->stream));
+    return 0;
+}
+
 void fr_dev_dataset_destroy(fr_dev_dataset *ds) {
     if (!ds) return;
     cudaSetDevice(ds->device);

@@ -252,6 +252,7 @@ struct fr_dev_dataset {
     DevBuf<float> gain;     // [n] by position
     DevBuf<double> gexp;    // [n] by position
     DevBuf<uint32_t> inst_of_pos_dev;
+    DevBuf<uint32_t> len_pos;    // optional, by position: features below this id are present in the row (libsvm data)
     std::vector<uint32_t> inst_of_pos, pos_of_inst;
     std::vector<uint32_t> q_start, q_len;  // per query, in positions
     std::vector<float> gain_pos;           // host copy, by position

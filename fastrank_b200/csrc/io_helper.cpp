@@ -41,11 +41,19 @@ F sym(void *h, const char *name) {
 }
 
 std::string read_plain(const std::string &path) {
-    std::ifstream in(path, std::ios::binary);
-    if (!in) not_found(path);
-    std::stringstream buf;
-    buf << in.rdbuf();
-    return buf.str();
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) not_found(path);
+    std::string out;
+    if (fseek(f, 0, SEEK_END) == 0) {
+        const long size = ftell(f);
+        if (size > 0) out.reserve((size_t)size);
+        fseek(f, 0, SEEK_SET);
+    }
+    std::vector<char> buf((size_t)4 << 20);
+    size_t n;
+    while ((n = fread(buf.data(), 1, buf.size(), f)) > 0) out.append(buf.data(), n);
+    fclose(f);
+    return out;
 }
 
 // ---- gzip (zlib's gz* layer reads concatenated members like flate2's MultiGzDecoder) ----

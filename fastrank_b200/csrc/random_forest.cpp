@@ -328,7 +328,7 @@ std::unique_ptr<TreeNode> learn_tree_device(const Ctx &c, fr_dev_rf *rf, const s
     std::vector<uint64_t> node_n;
     std::vector<int64_t> node_sum, b_sum, b_sq;
     std::vector<float> gmin, gmax, fmin, fmax;
-    std::vector<uint32_t> b_n, b_pos, t_fid;
+    std::vector<uint32_t> b_n, b_pos, t_fid, f_present;
     std::vector<double> t_split;
     std::vector<int32_t> t_left, t_right;
     while (!active.empty()) {
@@ -344,8 +344,9 @@ std::unique_ptr<TreeNode> learn_tree_device(const Ctx &c, fr_dev_rf *rf, const s
         b_pos.assign((size_t)na * F * k, 0);
         b_sum.assign((size_t)na * F * k, 0);
         b_sq.assign((size_t)na * F * k, 0);
+        f_present.assign((size_t)na * F, 0);
         if (fr_dev_rf_level_stats(rf, na, k, node_n.data(), node_sum.data(), gmin.data(), gmax.data(), fmin.data(),
-                                  fmax.data(), b_n.data(), b_pos.data(), b_sum.data(), b_sq.data()))
+                                  fmax.data(), b_n.data(), b_pos.data(), b_sum.data(), b_sq.data(), f_present.data()))
             throw Error(fr_dev_last_error());
         t_fid.assign(na, 0xffffffffu);
         t_split.assign(na, 0.0);
@@ -362,6 +363,9 @@ std::unique_ptr<TreeNode> learn_tree_device(const Ctx &c, fr_dev_rf *rf, const s
             // label_stats (:217-221) and FeatureStats.finish() both need more than one instance
             if (n > 1 && gmax[a] != gmin[a]) {
                 for (size_t fa = 0; fa < F; ++fa) {
+                    // FeatureStats.finish(): a feature fewer than two of the node's rows carry has no
+                    // statistics and proposes no split (normalizers.rs:29-35, random_forest.rs:387-391)
+                    if (f_present[(size_t)a * F + fa] < 2) continue;
                     const double lo = (double)fmin[(size_t)a * F + fa];
                     const double range = (double)fmax[(size_t)a * F + fa] - lo;
                     const size_t base = ((size_t)a * F + fa) * k;
@@ -483,13 +487,15 @@ Model random_forest_learn(const RandomForestParams &p, const DatasetView &view, 
     });
     if (all_features.empty()) throw Error("dataset has no features");
 
-    // Where do the per-level statistics come from?  The device path needs a dense source (no
-    // missing values) and labels that are exact in its integer unit; FASTRANK_RF=host / gpu
-    // overrides the size heuristic.
-    bool on_device = parent.dense_source && view.num_instances() >= 50000;
+    // Where do the per-level statistics come from?  The device path takes from_numpy data and
+    // libsvm data whose rows are all Dense32 (a row's missing features are then "ids beyond its
+    // length", which the device knows through fr_dev_dataset_set_row_lengths); it needs labels that
+    // are exact in its integer unit; FASTRANK_RF=host / gpu overrides the size heuristic.
+    const bool device_capable = parent.dense_source || parent.sparse_ids.empty();
+    bool on_device = device_capable && view.num_instances() >= 50000;
     if (const char *env = getenv("FASTRANK_RF")) {
         if (std::string(env) == "host") on_device = false;
-        if (std::string(env) == "gpu") on_device = parent.dense_source;
+        if (std::string(env) == "gpu") on_device = device_capable;
     }
     if (on_device) {
         const double unit = (double)(1 << FR_RF_GAIN_BITS);

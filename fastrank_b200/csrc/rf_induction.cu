@@ -31,6 +31,8 @@ struct RfLevel {
     const float *x;
     size_t ld;
     const float *gain;        // by position
+    const uint32_t *len_pos;  // nullptr, or by position: feature ids >= len_pos[p] are missing in that row
+    unsigned *f_present;      // [n_active][F] instances that carry the feature (written when len_pos is set)
     const uint32_t *samp_pos; // [m] position of every sampled instance
     const int *node_of;       // [m] active node of the instance, -1 = settled in a leaf
     uint32_t m;
@@ -53,9 +55,13 @@ __global__ void __launch_bounds__(kRfThreads) rf_minmax_kernel(RfLevel L) {
     int *sgmn = smx + L.n_active, *sgmx = sgmn + L.n_active;
     unsigned *scnt = (unsigned *)(sgmx + L.n_active);
     long long *ssum = (long long *)(scnt + L.n_active + (L.n_active & 1));
+    unsigned *sfp = (unsigned *)(ssum + L.n_active);  // instances of the node that carry this feature
+    const bool sparse = L.len_pos != nullptr;
+    const uint32_t fid = L.feats[f];
     for (uint32_t a = threadIdx.x; a < L.n_active; a += blockDim.x) {
         smn[a] = INT_MAX;
         smx[a] = INT_MIN;
+        sfp[a] = 0u;
         if (labels) {
             sgmn[a] = INT_MAX;
             sgmx[a] = INT_MIN;
@@ -75,12 +81,16 @@ __global__ void __launch_bounds__(kRfThreads) rf_minmax_kernel(RfLevel L) {
         __match_all_sync(0xffffffffu, nid, &uniform);
         if (uniform && nid < 0) continue;
         const uint32_t p = nid >= 0 ? L.samp_pos[i] : 0u;
+        // normalizers.rs:21-27: a row that does not carry the feature is left out of its min / max
+        const bool present = nid >= 0 && (!sparse || fid < __ldg(L.len_pos + p));
         const int o = nid >= 0 ? ford(__ldg(row + p)) : 0;
         const float g = (labels && nid >= 0) ? __ldg(L.gain + p) : 0.f;
         const int og = ford(g);
         const int y = (int)__double2ll_rn((double)g * kGainScale);  // |label| <= 16: fits easily
         if (uniform) {
-            const int wmn = __reduce_min_sync(0xffffffffu, o), wmx = __reduce_max_sync(0xffffffffu, o);
+            const int wmn = __reduce_min_sync(0xffffffffu, present ? o : INT_MAX);
+            const int wmx = __reduce_max_sync(0xffffffffu, present ? o : INT_MIN);
+            const unsigned npresent = (unsigned)__popc(__ballot_sync(0xffffffffu, present));
             int gmn = 0, gmx = 0, ys = 0;
             if (labels) {
                 gmn = __reduce_min_sync(0xffffffffu, og);
@@ -88,8 +98,11 @@ __global__ void __launch_bounds__(kRfThreads) rf_minmax_kernel(RfLevel L) {
                 ys = __reduce_add_sync(0xffffffffu, y);
             }
             if ((threadIdx.x & 31) == 0) {
-                atomicMin(&smn[nid], wmn);
-                atomicMax(&smx[nid], wmx);
+                if (npresent) {
+                    atomicMin(&smn[nid], wmn);
+                    atomicMax(&smx[nid], wmx);
+                    if (sparse) atomicAdd(&sfp[nid], npresent);
+                }
                 if (labels) {
                     atomicMin(&sgmn[nid], gmn);
                     atomicMax(&sgmx[nid], gmx);
@@ -98,8 +111,11 @@ __global__ void __launch_bounds__(kRfThreads) rf_minmax_kernel(RfLevel L) {
                 }
             }
         } else if (nid >= 0) {
-            atomicMin(&smn[nid], o);
-            atomicMax(&smx[nid], o);
+            if (present) {
+                atomicMin(&smn[nid], o);
+                atomicMax(&smx[nid], o);
+                if (sparse) atomicAdd(&sfp[nid], 1u);
+            }
             if (labels) {
                 atomicMin(&sgmn[nid], og);
                 atomicMax(&sgmx[nid], og);
@@ -114,6 +130,7 @@ __global__ void __launch_bounds__(kRfThreads) rf_minmax_kernel(RfLevel L) {
             atomicMin(&L.fmin[(size_t)a * L.F + f], smn[a]);
             atomicMax(&L.fmax[(size_t)a * L.F + f], smx[a]);
         }
+        if (sparse && sfp[a]) atomicAdd(&L.f_present[(size_t)a * L.F + f], sfp[a]);
         if (labels && scnt[a]) {
             atomicMin(&L.gmin[a], sgmn[a]);
             atomicMax(&L.gmax[a], sgmx[a]);
@@ -298,7 +315,7 @@ int fr_dev_rf_begin_tree(fr_dev_rf *rf, const uint32_t *instances, size_t m, con
 
 int fr_dev_rf_level_stats(fr_dev_rf *rf, uint32_t n_active, uint32_t k, uint64_t *node_n, int64_t *node_sum,
                           float *gmin, float *gmax, float *fmin, float *fmax, uint32_t *b_n, uint32_t *b_pos,
-                          int64_t *b_sum, int64_t *b_sq) {
+                          int64_t *b_sum, int64_t *b_sq, uint32_t *f_present) {
     if (!rf || n_active == 0 || k < 2) return fail("fr_dev_rf_level_stats: bad argument");
     fr_dev_dataset *ds = rf->ds;
     CU(cudaSetDevice(ds->device));
@@ -308,7 +325,7 @@ int fr_dev_rf_level_stats(fr_dev_rf *rf, uint32_t n_active, uint32_t k, uint64_t
     const size_t o_node_n = 0, o_node_sum = o_node_n + 8 * (size_t)n_active, o_bsum = o_node_sum + 8 * (size_t)n_active,
                  o_bsq = o_bsum + 8 * cells, o_fmin = o_bsq + 8 * cells, o_fmax = o_fmin + 4 * nf,
                  o_gmin = o_fmax + 4 * nf, o_gmax = o_gmin + 4 * (size_t)n_active, o_bn = o_gmax + 4 * (size_t)n_active,
-                 o_bpos = o_bn + 4 * cells, total = o_bpos + 4 * cells;
+                 o_bpos = o_bn + 4 * cells, o_fp = o_bpos + 4 * cells, total = o_fp + 4 * nf;
     CU(rf->stats.ensure(total));
     unsigned char *b = rf->stats.p;
     CU(cudaMemsetAsync(b, 0, total, s));
@@ -326,6 +343,8 @@ int fr_dev_rf_level_stats(fr_dev_rf *rf, uint32_t n_active, uint32_t k, uint64_t
     L.x = ds->x.p;
     L.ld = ds->ld;
     L.gain = ds->gain.p;
+    L.len_pos = ds->len_pos.n ? ds->len_pos.p : nullptr;
+    L.f_present = (unsigned *)(b + o_fp);
     L.samp_pos = rf->samp_pos.p;
     L.node_of = rf->node_of.p;
     L.m = rf->m;
@@ -346,7 +365,7 @@ int fr_dev_rf_level_stats(fr_dev_rf *rf, uint32_t n_active, uint32_t k, uint64_t
     const dim3 grid((rf->m + kChunk - 1) / kChunk, rf->F);
     if (rf->m > 0) {
         const size_t smem1 = sizeof(int) * 4 * (size_t)n_active + sizeof(unsigned) * ((size_t)n_active + 1) +
-                             sizeof(long long) * (size_t)n_active + 16;
+                             sizeof(long long) * (size_t)n_active + sizeof(unsigned) * (size_t)n_active + 16;
         if (smem1 > 200 * 1024) return fail("fr_dev_rf_level_stats: too many active nodes");
         if (smem1 > 48 * 1024)
             CU(cudaFuncSetAttribute(rf_minmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -373,6 +392,13 @@ int fr_dev_rf_level_stats(fr_dev_rf *rf, uint32_t n_active, uint32_t k, uint64_t
     memcpy(b_sq, host.data() + o_bsq, 8 * cells);
     memcpy(b_n, host.data() + o_bn, 4 * cells);
     memcpy(b_pos, host.data() + o_bpos, 4 * cells);
+    if (f_present) {
+        if (L.len_pos) {
+            memcpy(f_present, host.data() + o_fp, 4 * nf);
+        } else {  // nothing is missing: every instance of the node carries every feature
+            for (size_t i = 0; i < nf; ++i) f_present[i] = (uint32_t)node_n[i / rf->F];
+        }
+    }
     auto unord = [](int i) {
         const int j = i >= 0 ? i : i ^ 0x7fffffff;
         float f;

@@ -148,6 +148,12 @@ int fr_dev_device_count(void);
  * 1024 documents) are ranked in shared memory, longer ones from HBM. */
 int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const float *gains,
                           const uint32_t *query_index, uint32_t n_queries, fr_dev_dataset **out);
+/* Optional, for data loaded from libsvm files (instance.rs:104-122): row_len[i] = number of leading
+ * feature ids instance i carries (a dense row of max own id + 1 entries); ids at or beyond it are
+ * MISSING for that instance -- they read as 0.0 when scored or split on (model.rs:75,
+ * random_forest.rs:228) but are skipped by FeatureStats (normalizers.rs:21-27), which is what the
+ * random-forest statistics below honour.  Without this call nothing is missing. */
+int fr_dev_dataset_set_row_lengths(fr_dev_dataset *ds, const uint32_t *row_len);
 void fr_dev_dataset_destroy(fr_dev_dataset *ds);
 size_t fr_dev_dataset_bytes(const fr_dev_dataset *ds); /* HBM footprint */
 
@@ -267,10 +273,12 @@ int fr_dev_rf_begin_tree(fr_dev_rf *rf, const uint32_t *instances, size_t m, con
  *   b_n, b_pos, b_sum, b_sq [n_active][n_features][k]
  *        per bucket between consecutive thresholds i/k * (max - min) + min, i = 1..k-1
  *        (bucket b holds the values v with threshold_b <= v < threshold_{b+1}):
- *        instances, instances with label > 0, label sum, sum of squared labels */
+ *        instances, instances with label > 0, label sum, sum of squared labels
+ *   f_present [n_active][n_features]       NULL, or: instances of the node that carry the feature
+ *        (== node_n unless row lengths were set); fmin / fmax range over those only */
 int fr_dev_rf_level_stats(fr_dev_rf *rf, uint32_t n_active, uint32_t k, uint64_t *node_n, int64_t *node_sum,
                           float *gmin, float *gmax, float *fmin, float *fmax, uint32_t *b_n, uint32_t *b_pos,
-                          int64_t *b_sum, int64_t *b_sq);
+                          int64_t *b_sum, int64_t *b_sq, uint32_t *f_present);
 /* Per active node: fid (0xffffffff: the node is a leaf) and threshold; instances with
  * value < split move to node left[.], the others to right[.] (ids of the next level, -1 for a
  * child that is a leaf already). */

@@ -273,3 +273,38 @@ def test_compressed_inputs_by_extension(fr, golden_dir, tmp_path):
         fr.CQRel.load_file(str(bad))
     with pytest.raises(Exception, match="No such file"):
         fr.CDataset.open_ranksvm(str(tmp_path / "missing.gz"))
+
+
+def test_large_libsvm_file_is_parsed_in_slices(fr, tmp_path):
+    """Files of a few MB are cut at line boundaries and parsed by several threads: instance ids,
+    query grouping and the first error (with its line number) must be those of a sequential read."""
+    import numpy as np
+
+    rng = np.random.default_rng(3)
+    n, d = 30000, 24
+    qid = np.sort(rng.integers(0, 900, n))
+    X = np.round(rng.normal(size=(n, d)), 4).astype(np.float32)
+    y = rng.integers(0, 5, n)
+    lines = ["%d qid:%d %s # doc%d" % (y[i], qid[i], " ".join("%d:%r" % (j + 1, float(X[i, j])) for j in range(d)), i)
+             for i in range(n)]
+    text = "\n".join(lines) + "\n"
+    assert len(text) > 4 << 20
+    p = tmp_path / "big.libsvm"
+    p.write_text(text)
+    ds = fr.CDataset.open_ranksvm(str(p))
+    assert ds.num_instances() == n and ds.num_features() == d + 1
+    by_q = ds.instances_by_query()
+    assert len(by_q) == len(np.unique(qid))
+    for q in (int(qid[0]), int(qid[n // 2]), int(qid[-1])):
+        assert by_q[str(q)] == [int(i) for i in np.nonzero(qid == q)[0]]
+    # an error two thirds into the file is reported with its own line number
+    bad_line = 2 * n // 3
+    lines[bad_line] = "1 qid:7 3:what"
+    (tmp_path / "big_bad.libsvm").write_text("\n".join(lines) + "\n")
+    with pytest.raises(Exception, match=r"LineParseError\(%d, FeatureValNotFloat" % (bad_line + 1)):
+        fr.CDataset.open_ranksvm(str(tmp_path / "big_bad.libsvm"))
+    # two errors: the earlier one wins
+    lines[100] = "nope qid:7 3:1"
+    (tmp_path / "big_bad2.libsvm").write_text("\n".join(lines) + "\n")
+    with pytest.raises(Exception, match=r"LineParseError\(101, Label"):
+        fr.CDataset.open_ranksvm(str(tmp_path / "big_bad2.libsvm"))

@@ -672,3 +672,33 @@ def test_trecrun_success_path_with_docids_and_a_sparse_row(fr, oracle, tmp_path)
     assert any(r[2] == "sparse-doc" for r in rows) or True
     sub = ds.subsample_queries(["q1", "q3"])
     assert sub.predict_trecrun(m, str(tmp_path / "sub.trecrun")) == sum(1 for q in qids if q in ("q1", "q3"))
+
+
+@pytest.mark.parametrize("where", ["host", "gpu"])
+def test_random_forest_golden_with_missing_features_on_either_path(fr, goldens, golden_dir, oracle, trec_train,
+                                                                 monkeypatch, where):
+    """The reference's determinism golden (random_forest.rs:427-463) is defined on libsvm data in
+    which 13 rows do not carry the last feature: FeatureStats skip them (normalizers.rs:21-27),
+    splits read them as 0.0.  The per-level statistics come from the host passes or from the GPU
+    (which learns each row's length through fr_dev_dataset_set_row_lengths): same forest."""
+    from oracle import random_forest_oracle as rfo
+
+    monkeypatch.setenv("FASTRANK_RF", where)
+    ds = fr.CDataset.open_ranksvm(os.path.join(golden_dir, "trec_news_2018.train"),
+                                  os.path.join(golden_dir, "trec_news_2018.features.json"))
+    req = _rf_req(fr)
+    model = ds.train_model(req)
+    ndcg = np.mean(list(ds.evaluate(model, "ndcg@5").values()))
+    assert ndcg == pytest.approx(goldens["rf_determinism_ndcg5"]["expected"], abs=1e-9)
+    exp_spec = rfo.learn_forest(trec_train, goldens["rf_determinism_ndcg5"]["params"])
+    assert oracle.score_model(trec_train.X, exp_spec).tolist() == model.predict_dense(ds).tolist()
+    # the notebook's forest as well (100 trees, other sampling rates)
+    g = goldens["notebook_random_forest"]
+    req = fr.TrainRequest.random_forest()
+    for k, v in g["params"].items():
+        setattr(req.params, k, v)
+    req.params.quiet = True
+    test_ds = fr.CDataset.open_ranksvm(os.path.join(golden_dir, "trec_news_2018.test"),
+                                       os.path.join(golden_dir, "trec_news_2018.features.json"))
+    rf = ds.train_model(req)
+    assert "%.3g" % np.mean(list(test_ds.evaluate(rf, "NDCG@5").values())) == g["test_ndcg5_printed"]
