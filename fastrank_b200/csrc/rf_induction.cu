@@ -149,15 +149,14 @@ __global__ void __launch_bounds__(kRfThreads) rf_bucket_kernel(RfLevel L) {
     extern __shared__ long long sm64[];
     const uint32_t f = blockIdx.y, k = L.k;
     const size_t cells = (size_t)L.n_active * k;
-    long long *ssum = sm64, *ssq = sm64 + cells;
-    unsigned *sn = (unsigned *)(ssq + cells), *spos = sn + cells;
+    // Shared-memory cell = four 32-bit words (64-bit shared-memory atomics are several times
+    // slower than 32-bit ones here): a CTA sees at most kChunk = 2048 instances and |y| <= 2^16, so
+    //   [0] instances | instances with label > 0 << 16    [1] sum of y (signed)
+    //   [2] sum of (y^2 & 0xffff)                          [3] sum of (y^2 >> 16)
+    // all stay below 2^31.
+    unsigned *scell = (unsigned *)sm64;
     if (SMEM) {
-        for (size_t c = threadIdx.x; c < cells; c += blockDim.x) {
-            ssum[c] = 0;
-            ssq[c] = 0;
-            sn[c] = 0;
-            spos[c] = 0;
-        }
+        for (size_t c = threadIdx.x; c < 4 * cells; c += blockDim.x) scell[c] = 0u;
         __syncthreads();
     }
     const float *__restrict__ row = L.x + (size_t)L.feats[f] * L.ld;
@@ -198,12 +197,11 @@ __global__ void __launch_bounds__(kRfThreads) rf_bucket_kernel(RfLevel L) {
                 const unsigned qlo = __reduce_add_sync(0xffffffffu, me ? (unsigned)(sq64 & 0xffff) : 0u);
                 const unsigned qhi = __reduce_add_sync(0xffffffffu, me ? (unsigned)(sq64 >> 16) : 0u);
                 if ((threadIdx.x & 31) == 0) {
-                    const size_t cell = (size_t)nid * k + bb;
-                    atomicAdd(&sn[cell], (unsigned)cnt);
-                    if (npos) atomicAdd(&spos[cell], (unsigned)npos);
-                    atomicAdd((unsigned long long *)&ssum[cell], (unsigned long long)(long long)ys);
-                    atomicAdd((unsigned long long *)&ssq[cell],
-                              (unsigned long long)(((long long)qhi << 16) + (long long)qlo));
+                    unsigned *cell = scell + 4 * ((size_t)nid * k + bb);
+                    atomicAdd(cell + 0, (unsigned)cnt | ((unsigned)npos << 16));
+                    atomicAdd(cell + 1, (unsigned)ys);
+                    atomicAdd(cell + 2, qlo);
+                    atomicAdd(cell + 3, qhi);
                 }
             }
             continue;
@@ -212,10 +210,12 @@ __global__ void __launch_bounds__(kRfThreads) rf_bucket_kernel(RfLevel L) {
         const long long yl = (long long)y;
         const size_t cell = (size_t)nid * k + b;
         if (SMEM) {
-            atomicAdd(&sn[cell], 1u);
-            if (positive) atomicAdd(&spos[cell], 1u);
-            atomicAdd((unsigned long long *)&ssum[cell], (unsigned long long)yl);
-            atomicAdd((unsigned long long *)&ssq[cell], (unsigned long long)(yl * yl));
+            unsigned *sc = scell + 4 * cell;
+            const unsigned long long sq = (unsigned long long)(yl * yl);
+            atomicAdd(sc + 0, positive ? 0x10001u : 1u);
+            atomicAdd(sc + 1, (unsigned)y);
+            atomicAdd(sc + 2, (unsigned)(sq & 0xffffu));
+            atomicAdd(sc + 3, (unsigned)(sq >> 16));
         } else {
             const size_t gc = ((size_t)nid * L.F + f) * k + b;
             atomicAdd(&L.b_n[gc], 1u);
@@ -227,13 +227,15 @@ __global__ void __launch_bounds__(kRfThreads) rf_bucket_kernel(RfLevel L) {
     if (SMEM) {
         __syncthreads();
         for (size_t c = threadIdx.x; c < cells; c += blockDim.x) {
-            if (!sn[c]) continue;
+            const unsigned *sc = scell + 4 * c;
+            const unsigned n_c = sc[0] & 0xffffu, pos_c = sc[0] >> 16;
+            if (!n_c) continue;
             const size_t nid = c / k, b = c % k;
             const size_t gc = (nid * L.F + f) * k + b;
-            atomicAdd(&L.b_n[gc], sn[c]);
-            if (spos[c]) atomicAdd(&L.b_pos[gc], spos[c]);
-            atomicAdd((unsigned long long *)&L.b_sum[gc], (unsigned long long)ssum[c]);
-            atomicAdd((unsigned long long *)&L.b_sq[gc], (unsigned long long)ssq[c]);
+            atomicAdd(&L.b_n[gc], n_c);
+            if (pos_c) atomicAdd(&L.b_pos[gc], pos_c);
+            atomicAdd((unsigned long long *)&L.b_sum[gc], (unsigned long long)(long long)(int)sc[1]);
+            atomicAdd((unsigned long long *)&L.b_sq[gc], ((unsigned long long)sc[3] << 16) + (unsigned long long)sc[2]);
         }
     }
 }
@@ -372,7 +374,7 @@ int fr_dev_rf_level_stats(fr_dev_rf *rf, uint32_t n_active, uint32_t k, uint64_t
         rf_minmax_kernel<<<grid, kRfThreads, smem1, s>>>(L);
         LAUNCHED();
         CU(cudaGetLastError());
-        const size_t smem2 = (size_t)n_active * k * 24;
+        const size_t smem2 = (size_t)n_active * k * 16;
         if (smem2 <= 96 * 1024) {
             if (smem2 > 48 * 1024)
                 CU(cudaFuncSetAttribute(rf_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
