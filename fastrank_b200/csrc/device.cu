@@ -327,6 +327,22 @@ __host__ __device__ constexpr size_t eval_smem_bytes_c(int kc, int tb) {
     return ((8 * eval_words(kc, tb) + 4 * (size_t)tb + 4 * 32 + 2 * (size_t)tb) + 15) / 16 * 16;
 }
 
+// tk[k] += x * w[k] for the KC weight vectors of one feature: separate multiply and add
+// (dense_dataset.rs:67-76), weights read in pairs
+template <int KC>
+__device__ __forceinline__ void accumulate_feature(double (&tk)[KC], double xv, const double *__restrict__ wj) {
+    if (KC == 1) {
+        tk[0] = __dadd_rn(tk[0], __dmul_rn(xv, wj[0]));
+    } else {
+#pragma unroll
+        for (int k = 0; k + 1 < KC; k += 2) {
+            const double2 w2 = *reinterpret_cast<const double2 *>(wj + k);
+            tk[k] = __dadd_rn(tk[k], __dmul_rn(xv, w2.x));
+            tk[k + 1] = __dadd_rn(tk[k + 1], __dmul_rn(xv, w2.y));
+        }
+    }
+}
+
 // evaluate_mean for KC arbitrary weight vectors in one pass over X (evaluators.rs:173-224).
 // One thread scores one document for all KC candidates: x_j is read once (coalesced along the
 // document axis of the feature-major matrix), the KC weights of feature j come from shared
@@ -381,13 +397,7 @@ __global__ void __launch_bounds__(TB) linear_batch_kernel(PlanView P, BatchArgs 
 #pragma unroll
                     for (int u = 0; u < XB; ++u) {
                         const double xv = (double)buf[u];
-                        const double *wj = s_w + (size_t)(blk * XB + u) * KC;
-#pragma unroll
-                        for (int k = 0; k < KC; k += 2) {
-                            const double2 w2 = *reinterpret_cast<const double2 *>(wj + k);
-                            tk[k] = __dadd_rn(tk[k], __dmul_rn(xv, w2.x));
-                            tk[k + 1] = __dadd_rn(tk[k + 1], __dmul_rn(xv, w2.y));
-                        }
+                        accumulate_feature<KC>(tk, xv, s_w + (size_t)(blk * XB + u) * KC);
                     }
                 };
                 load(xa, 0);
@@ -414,13 +424,7 @@ __global__ void __launch_bounds__(TB) linear_batch_kernel(PlanView P, BatchArgs 
                     for (int u = 0; u < XB; ++u) {
                         if (j + u < n) {
                             const double xv = (double)xt[u];
-                            const double *wj = s_w + (size_t)(j + u) * KC;
-#pragma unroll
-                            for (int k = 0; k < KC; k += 2) {
-                                const double2 w2 = *reinterpret_cast<const double2 *>(wj + k);
-                                tk[k] = __dadd_rn(tk[k], __dmul_rn(xv, w2.x));
-                                tk[k + 1] = __dadd_rn(tk[k + 1], __dmul_rn(xv, w2.y));
-                            }
+                            accumulate_feature<KC>(tk, xv, s_w + (size_t)(j + u) * KC);
                         }
                     }
                 }
@@ -824,6 +828,17 @@ int launch_batch(fr_dev_plan *pl, int kc, int tb, const BatchArgs &args_in, cuda
                                                            32768u / (uint32_t)(kc * sizeof(double))));
     const size_t smem = eval_smem_bytes(kc, tb) + (size_t)args.wchunk * kc * sizeof(double);
     PlanView pv = pl->view();
+    if (kc == 1 && tb == 128) {  // a single weight vector: the HBM-bound case gets its own instance
+        uint32_t gx = 1;
+        if (grid_for(linear_batch_kernel<1, 128>, 128, smem, pl->sm_count, pl->nt, 1, &gx)) return 1;
+        auto *ev = pl->ds->prof_slot();
+        if (ev) cudaEventRecord(ev->first, stream);
+        linear_batch_kernel<1, 128><<<gx, 128, smem, stream>>>(pv, args);
+        if (ev) cudaEventRecord(ev->second, stream);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        return 0;
+    }
     DISPATCH_ALL({
         uint32_t gx = 1;
         if (grid_for(linear_batch_kernel<KC, TB>, TB, smem, pl->sm_count, pl->nt, 1, &gx)) return 1;
@@ -1345,7 +1360,9 @@ int fr_dev_eval_linear_batch(fr_dev_plan *pl, const double *w, size_t wlen, size
     std::vector<double> wt;
     for (size_t c0 = 0; c0 < n_cand; c0 += cap) {
         const int K = (int)std::min<size_t>(cap, n_cand - c0);
-        const int kc = pick_kc(K, pl->tb);
+        const char *tma_on = getenv("FASTRANK_TMA_EVAL");  // the TMA variant is built for 2 / 4 / 8 vectors
+        const bool single = K == 1 && pl->tb == 128 && !getenv("FASTRANK_NO_KC1") && !(tma_on && atoi(tma_on) != 0);
+        const int kc = single ? 1 : pick_kc(K, pl->tb);
         wt.assign((size_t)std::max<uint32_t>(dm, 1) * kc, 0.0);
         for (uint32_t j = 0; j < dm; ++j)
             for (int k = 0; k < K; ++k) wt[(size_t)j * kc + k] = w[(c0 + k) * wlen + j];
