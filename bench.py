@@ -454,7 +454,7 @@ def run_ours(args, rank, world, local_rank):
             dev.profile(False)
             algo = n_local * d * 4 + n_local * 4 + (nq_local + 1) * 4 + c * d * 8 + c * 8
             gbs = algo / (l_ms / max(n_l, 1) / 1e3) / 1e9
-            full_rescore.append({"kernel": "linear_batch_kernel<%d,%d>" % (max(c, 2), plan_layout[0]),
+            full_rescore.append({"kernel": "linear_batch_kernel<%d,%d>" % (c if plan_layout[0] == 128 else max(c, 2), plan_layout[0]),
                                  "weight_vectors_per_pass": c, "avg_launch_ms": l_ms / max(n_l, 1),
                                  "evals_per_s": c / (l_ms / max(n_l, 1) / 1e3),
                                  "algorithmic_bytes_per_launch": algo, "achieved": gbs, "unit": "GB/s",
