@@ -471,7 +471,7 @@ def test_training_schedules_agree(fr, monkeypatch):
     req.measure = "ndcg@10"
     req.params.num_restarts, req.params.seed, req.params.quiet = 3, 11, True
     results = {}
-    for label, env in (("default", {}), ("lookahead", {"FASTRANK_LOOKAHEAD": "1"}),
+    for label, env in (("default", {}), ("no_lookahead", {"FASTRANK_LOOKAHEAD": "0"}),
                        ("no_speculation", {"FASTRANK_SPECULATE": "0"}), ("exact", {"FASTRANK_SWEEP": "exact"})):
         for k in ("FASTRANK_LOOKAHEAD", "FASTRANK_SPECULATE", "FASTRANK_SWEEP"):
             monkeypatch.delenv(k, raising=False)
@@ -481,11 +481,11 @@ def test_training_schedules_agree(fr, monkeypatch):
         stats = fr.query_json("last_train_stats")
         results[label] = (model.to_dict()["Linear"]["weights"], stats["evals_consumed"], stats["global_steps"])
     base = results["no_speculation"]
-    for label in ("default", "lookahead", "exact"):
+    for label in ("default", "no_lookahead", "exact"):
         assert results[label][0] == base[0], label
         assert results[label][1] == base[1], label
-    # and the schedules really differ in how many launches they need
-    assert results["lookahead"][2] <= results["default"][2] < results["no_speculation"][2]
+    # and the schedules really differ in how many launches they need (lookahead is on by default)
+    assert results["default"][2] <= results["no_lookahead"][2] < results["no_speculation"][2]
 
 
 @pytest.mark.parametrize("where", ["host", "gpu"])
