@@ -174,9 +174,12 @@ Model coordinate_ascent_learn(const CoordinateAscentParams &p, const DatasetView
         if (active.empty()) break;
         // 1. every active restart prepares its next group(s) of candidates
         sweeps.clear();
-        const size_t extra = lookahead && active.size() < kLaunchSweeps ? kLaunchSweeps / active.size() - 1 : 0;
+        // idle sweep slots of the launch are dealt out to the active restarts, one more line search
+        // each, the first restarts taking what does not divide evenly
+        const size_t idle = lookahead && active.size() < kLaunchSweeps ? kLaunchSweeps - active.size() : 0;
         for (size_t a = 0; a < active.size(); ++a) {
             Restart &r = *active[a];
+            const size_t extra = idle / active.size() + (a < idle % active.size() ? 1 : 0);
             if (r.group == 0) {
                 if (r.fi == 0) {
                     r.order = fids;
