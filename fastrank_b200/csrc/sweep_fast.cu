@@ -852,6 +852,12 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
     if (n_sweeps == 0) return 0;
     fr_dev_dataset *ds = pl->ds;
     FastPlan &fp = pl->fast;
+    static const bool trace_steps = getenv("FASTRANK_TRACE_STEPS") != nullptr;
+    static thread_local double tr_fill = 0, tr_submit = 0, tr_wait = 0, tr_between = 0, tr_copy = 0;
+    static thread_local uint64_t tr_calls = 0;
+    static thread_local std::chrono::steady_clock::time_point tr_last_exit;
+    const auto tr_enter = std::chrono::steady_clock::now();
+    if (trace_steps && tr_calls > 0) tr_between += std::chrono::duration<double, std::micro>(tr_enter - tr_last_exit).count();
     CU(cudaSetDevice(ds->device));
     cudaStream_t s = ds->stream;
     const size_t total = n_sweeps * cand_stride;
@@ -940,7 +946,12 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         CU(cudaMemsetAsync(pl->perq_dev.p, 0, sizeof(double) * total * (size_t)pl->nq_view, s));
     bool first_pass = true;
     for (;;) {
-        if (!first_pass) CU(cudaStreamSynchronize(s));  // the staging blob is about to be rewritten
+        if (!first_pass) {
+            bool more = false;  // rows left for another pass?
+            for (size_t sw = 0; sw < n_sweeps && !more; ++sw) more = cursor[sw] < n_cand[sw];
+            if (!more) break;
+            CU(cudaStreamSynchronize(s));  // the staging blob is about to be rewritten
+        }
         unsigned char *hp = fp.in_host.p;
         double *h_wt = (double *)hp;
         double *h_row_w = h_wt + wt_count;
@@ -976,7 +987,10 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
             for (size_t j = 0; j < dm; ++j) col[j * kMaxSweeps] = j == fid[sw] ? 0.0 : base_w[sw * wlen + j];
             h_fid[sw] = fid[sw];
         }
+        const auto tr_filled = std::chrono::steady_clock::now();
+        if (trace_steps) tr_fill += std::chrono::duration<double, std::micro>(tr_filled - tr_enter).count();
         CU(cudaMemcpyAsync(fp.in_dev.p, hp, in_bytes, cudaMemcpyHostToDevice, s));
+        if (trace_steps) tr_copy += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr_filled).count();
         if (!first_pass) CU(cudaMemsetAsync(ctr_dev, 0, sizeof(unsigned) * n_groups, s));
         first_pass = false;
         unsigned char *dp = fp.in_dev.p;
@@ -1069,6 +1083,7 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         if (rc) return 1;
     }
     if (direct) {
+        const auto tr_submitted = std::chrono::steady_clock::now();
         // spin on the flag the last CTA raises (a stream query now and then catches a failed launch)
         volatile unsigned *flag = (volatile unsigned *)(fp.pub_host + kPubErrOff + 4);
         const unsigned want = fp.pub_epoch;
@@ -1086,6 +1101,17 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
         }
         std::atomic_thread_fence(std::memory_order_acquire);
         fp.direct_open = false;
+        if (trace_steps) {
+            const auto tr_done = std::chrono::steady_clock::now();
+            tr_submit += std::chrono::duration<double, std::micro>(tr_submitted - tr_enter).count();
+            tr_wait += std::chrono::duration<double, std::micro>(tr_done - tr_submitted).count();
+            tr_last_exit = tr_done;
+            if (++tr_calls % 200 == 0) {
+                fprintf(stderr, "[fastrank_b200] sweep steps: fill %.1f us, H2D call %.1f us, fill+submit %.1f us, wait %.1f us, between calls %.1f us (avg of %llu)\n",
+                        tr_fill / tr_calls, tr_copy / tr_calls, tr_submit / tr_calls, tr_wait / tr_calls, tr_between / tr_calls,
+                        (unsigned long long)tr_calls);
+            }
+        }
         int err_flags;
         memcpy(&err_flags, fp.pub_host + kPubErrOff, sizeof(int));
         if (check_err_flags(err_flags)) return 1;
