@@ -35,6 +35,8 @@
 // oracle.  When the arithmetic is exact (e.g. dyadic weights on small-integer features, or an
 // all-zero base) the scores themselves are bit-identical, ties included.  The exact-order
 // kernel (device.cu coord_sweep_kernel) stays available behind fr_dev_eval_coord_sweeps.
+#include <sched.h>
+
 #include "device_common.cuh"
 
 namespace {
@@ -1098,6 +1100,7 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
 #if defined(__x86_64__)
             __builtin_ia32_pause();
 #endif
+            if ((spins & 0xff) == 0xff) sched_yield();  // one process per GPU: do not starve the other ranks' threads
         }
         std::atomic_thread_fence(std::memory_order_acquire);
         fp.direct_open = false;
