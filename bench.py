@@ -466,20 +466,11 @@ def run_ours(args, rank, world, local_rank):
     value = EVALS_PER_STEP * args.steps / (ms / 1e3)
 
     # multi-GPU parity, visible to the driver: the sharded sums of the first timed step (already
-    # all-reduced: identical on every rank) against a single-GPU plan over rank 0's FULL copy
-    dist_equal = None
+    # all-reduced: identical on every rank) are kept here and compared, AFTER the e2e region, with
+    # a single-GPU plan over rank 0's full copy
+    sharded = None
     if world > 1 and not args.exact:
         sharded = plan.coord_sweeps_packed(packed[args.warmup][0]).copy()
-        if rank == 0:
-            qidx_full, nq_full = dense_query_index(qid)
-            dev1 = DevDataset(X, y.astype(np.float32), qidx_full, nq_full, device=local_rank)
-            try:
-                plan1 = dev1.plan(0, DEPTH)
-                base, fids, ga, gb = step_inputs(args.warmup, d)
-                single = plan1.coord_sweeps_packed(plan1.pack_sweeps(base, fids, [a + b for a, b in zip(ga, gb)]))
-                dist_equal = bool(np.array_equal(single, sharded))
-            finally:
-                dev1.close()
 
     # roofline of the dominant kernel.  One launch of the batched sweep = ONE pass over this
     # rank's slice of the feature matrix serving all 8 restarts (204 or 200 candidates):
@@ -560,6 +551,20 @@ def run_ours(args, rank, world, local_rank):
            "what": "from_numpy + train_model(CA, 8 restarts, seed 42, to convergence) + evaluate through the C ABI"}
     del ds, model
     clocks = sampler.stop()  # sampled across both timed regions (device-timed steps and e2e)
+
+    dist_equal = None
+    if sharded is not None and rank == 0:
+        qidx_full, nq_full = dense_query_index(qid)
+        dev1 = DevDataset(X, y.astype(np.float32), qidx_full, nq_full, device=local_rank)
+        try:
+            plan1 = dev1.plan(0, DEPTH)
+            base, fids, ga, gb = step_inputs(args.warmup, d)
+            single = plan1.coord_sweeps_packed(plan1.pack_sweeps(base, fids, [a + b for a, b in zip(ga, gb)]))
+            dist_equal = bool(np.array_equal(single, sharded))
+        finally:
+            dev1.close()
+    if world > 1:
+        barrier()  # rank 0 may still be checking; nobody tears the communicator down before that
 
     # ---- CPU baseline on the host cores (rank 0, single-GPU run only) -----------------------
     cpu = None
