@@ -155,3 +155,59 @@ def test_full_size_forest_scoring(oracle):
     assert np.array_equal(fr.CModel.from_dict(ens(a)).predict_dense(ds), sa)
     rows = np.sort(rng.choice(N, 20000, replace=False))
     assert np.array_equal(sa[rows], oracle.score_model(np.ascontiguousarray(X[rows]), ens(a)))
+
+
+def test_full_size_packed_kernel_equals_general_kernel(full, monkeypatch):
+    """At full size: the register-packed NDCG@10 kernel (what train_model and bench.py launch) and
+    the general tile kernel produce the same 8 x 51 integer sums, bit for bit, with direct
+    publication of the sums on and off."""
+    X, y, qid, dev, nq = full
+    import bench
+
+    plan = dev.plan(0, 10)
+    base, fids, ga, gb = bench.step_inputs(5, D)
+    pk = plan.pack_sweeps(base, fids, [a + b for a, b in zip(ga, gb)])
+    got = {}
+    for label, env in (("packed", {}), ("tile", {"FASTRANK_SWEEP_KERNEL": "tile"}), ("undirect", {"FASTRANK_DIRECT": "0"})):
+        for k in ("FASTRANK_SWEEP_KERNEL", "FASTRANK_DIRECT"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got[label] = plan.coord_sweeps_packed(pk).copy()
+        assert np.array_equal(plan.coord_sweeps_packed(pk), got[label])  # repeatable (the kernel re-zeroes its state)
+    assert np.array_equal(got["packed"], got["tile"])
+    assert np.array_equal(got["packed"], got["undirect"])
+
+
+def test_long_list_shape_select_then_rank_equals_full_count(oracle, monkeypatch):
+    """BASELINE configs[4]'s list shape (~120 documents per query) at a size the test can afford:
+    the select-then-rank path of the packed kernel against the full count and the general kernel,
+    bit for bit, and against the oracle on a few candidates."""
+    import bench
+
+    n, q = 400_000, 3_300
+    X, y, qid = synth(n, D, q, seed=77)
+    qidx, nq = dense_query_index(qid)
+    dev = DevDataset(X, y.astype(np.float32), qidx, nq)
+    try:
+        plan = dev.plan(0, 10)
+        assert dev.lib.fr_dev_plan_tile_documents(plan.ptr) == 256
+        base, fids, ga, gb = bench.step_inputs(2, D)
+        cands = [a + b for a, b in zip(ga, gb)]
+        got = {}
+        for label, env in (("pruned", {}), ("full", {"FASTRANK_PRUNE_MIN": "0"}), ("tile", {"FASTRANK_SWEEP_KERNEL": "tile"})):
+            for k in ("FASTRANK_SWEEP_KERNEL", "FASTRANK_PRUNE_MIN"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got[label] = plan.coord_sweeps(base, fids, cands, fast=True).copy()
+        assert np.array_equal(got["pruned"], got["full"])
+        assert np.array_equal(got["pruned"], got["tile"])
+        ods = oracle_dataset(oracle, X, y, qid)
+        for r, k in ((0, 0), (4, 30), (7, 50)):
+            w = base[r].copy()
+            w[fids[r]] = cands[r][k]
+            exp = oracle.evaluate_scores(ods, oracle.score_linear(X, w), "ndcg@10")
+            assert abs(int(got["pruned"][r, k]) - fx_sum(exp)) / FX / nq < 1e-9
+    finally:
+        dev.close()
