@@ -16,7 +16,9 @@
 //     left-to-right f64 sum of (2^gain - 1) / log2(rank + 2) over ranks 0..k-1
 //     (evaluators.rs:255-272) from the host-built table -- and adds round(value * 2^40) to the
 //     row's sum.
-// Two barriers per tile instead of two per row group, ~0.55x the instructions.
+//   * lists of >= 48 documents are pruned per candidate before they are ranked (rank_pruned below).
+// Two barriers per tile instead of two per row group; 0.86 G warp instructions per 408-candidate
+// launch on 1M x 136 against 1.21 G, 0.98 ms against 1.66 ms (profiles/r02_sweep_packed_*).
 #pragma once
 
 // unroll factors of the two walk loops per chunk width (code size vs. latency hiding: at 4/4/4 the

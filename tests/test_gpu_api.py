@@ -702,3 +702,45 @@ def test_random_forest_golden_with_missing_features_on_either_path(fr, goldens, 
                                        os.path.join(golden_dir, "trec_news_2018.features.json"))
     rf = ds.train_model(req)
     assert "%.3g" % np.mean(list(test_ds.evaluate(rf, "NDCG@5").values())) == g["test_ndcg5_printed"]
+
+
+def test_concurrent_predict_and_evaluate_on_one_dataset(fr, oracle):
+    """Predict shares the dataset's stream and score scratch with the evaluators: calls from several
+    threads (cffi releases the GIL) with different models -- linear, forest, more models than the
+    per-dataset device-model cache holds -- must each get their own scores."""
+    import threading
+
+    X, y, qid = synth(20000, 12, 500, seed=33)
+    ds = fr.CDataset.from_numpy(X, y, qid)
+    rng = np.random.default_rng(2)
+
+    def tree(depth):
+        if depth == 0:
+            return {"LeafNode": float(np.round(rng.normal(), 3))}
+        fid = int(rng.integers(0, 12))
+        return {"FeatureSplit": {"fid": fid, "split": float(rng.choice(X[:, fid])), "lhs": tree(depth - 1), "rhs": tree(depth - 1)}}
+
+    specs = [{"Linear": {"weights": [float(v) for v in rng.normal(size=12)]}} for _ in range(4)]
+    specs += [{"Ensemble": {"weights": [1.0, 0.5], "models": [{"DecisionTree": tree(4)}, {"DecisionTree": tree(3)}]}} for _ in range(4)]
+    expected = [oracle.score_model(X, s) for s in specs]
+    models = [fr.CModel.from_dict(s) for s in specs]
+    errors = []
+
+    def work(i):
+        try:
+            for rep in range(8):
+                got = models[i].predict_dense(ds)
+                if not np.array_equal(got, expected[i]):
+                    errors.append((i, rep, "scores of another model"))
+                    return
+                if rep % 3 == 0:
+                    ds.evaluate_mean(models[(i + 1) % len(models)], "ndcg@10")
+        except Exception as e:  # pragma: no cover
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(specs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
