@@ -355,8 +355,10 @@ def side_mslr(steps=5, warmup=3):
                 "kernel_ms_per_launch": kernel_ms, "launches_per_step": n_k / steps,
                 "algorithmic_bytes_per_launch": algo, "achieved_GBps": algo / (kernel_ms / 1e3) / 1e9,
                 "frac_of_hbm_peak": algo / (kernel_ms / 1e3) / 1e9 / peak,
-                "bf16_gemm_variant": "not built: phase 1 (the 8-column X.W product a GEMM would replace) is a minor "
-                                     "share of this launch, see profiles/ and DESIGN.md"}
+                "bf16_gemm_variant": "not built: phase 1 (the 8-column X.W product a GEMM would replace) is 12.1 % of the "
+                                     "stall samples / 13.2 % of the instructions of this launch (16.7 % / 15.8 % on the "
+                                     "1M-document step), ncu source counters in profiles/r02_sweep_packed_*_hot_lines.txt; "
+                                     "bf16 inputs would also break the f64 rounding contract (DESIGN.md 8)"}
     finally:
         dev.close()
 
@@ -499,9 +501,10 @@ def run_ours(args, rank, world, local_rank):
                 else traffic["issue_active_pct"] / 100.0,
                 "fp64_pipe_busy_frac": None if traffic is None or "fp64_pipe_pct" not in traffic
                 else traffic["fp64_pipe_pct"] / 100.0,
-                "note": "one X pass is shared by all 8 restarts (204-408 candidate rankings per document per "
-                        "launch), so the kernel is instruction-issue / FP64-compare bound, not HBM bound; "
-                        "see DESIGN.md for the issue-slot roofline"}
+                "note": "one X pass is shared by all 8 restarts (408 candidate rankings per document per launch), so "
+                        "the kernel is FP64-compare bound, not HBM bound: ~240 M warp-level DSETP per launch at one "
+                        "per ~2.35 clocks per SM sub-partition (tools/micro/cmp_throughput.cu) plus phase 1 = 0.71 ms "
+                        "of FP64-pipe time; see DESIGN.md 3.0"}
     plan.close()
     dev.close()
 
