@@ -340,6 +340,7 @@ struct FastPlan {
     DevBuf<double> disc_tbl;         // [n_cls][tbl_r]  (2^gain - 1) / log2(r + 2)
     // NDCG@k with k <= 16 and <= 15 gain classes: sweep_packed_kernel (sweep_packed.cuh)
     bool packed_ok = false;
+    bool slots_ok = false;  // the same kernel with ranks filed in shared-memory slots: any measure, tiles <= 256
     DevBuf<uint32_t> pk_q_task_off;     // nq_plan + 1
     DevBuf<uint32_t> pk_tile_task_off;  // nt + 1
     DevBuf<uint4> pk_tasks;             // chunks of <= 16 documents, grouped by query (PackedView::tasks)

@@ -604,11 +604,11 @@ int launch_fast(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStrea
 
 #include "sweep_packed.cuh"
 
-template <int TB, bool WS, int MINB, int PS>
+template <int TB, bool WS, int MINB, int PS, bool SLOTS = false>
 int launch_packed(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStream_t stream) {
     const uint32_t dm8 = (a.dm + 7) & ~7u;
-    const PackedLayout L(TB, WS ? dm8 * kMaxSweeps : 0u, PS);
-    auto kernel = sweep_packed_kernel<TB, WS, MINB, PS>;
+    const PackedLayout L(TB, WS ? dm8 * kMaxSweeps : 0u, PS, SLOTS);
+    auto kernel = sweep_packed_kernel<TB, WS, MINB, PS, SLOTS>;
     static std::mutex mu;
     static std::map<std::pair<int, size_t>, int> cache;
     int occ = 0;
@@ -649,7 +649,7 @@ int launch_packed(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStr
     v.tile_task_off = pl->fast.pk_tile_task_off.p;
     v.tasks = pl->fast.pk_tasks.p;
     v.pd_cls = pl->fast.pd_cls.p;
-    v.tbl = pl->fast.pk_tbl.p;
+    v.tbl = pl->fast.pk_tbl.n ? pl->fast.pk_tbl.p : nullptr;
     v.tbl_r = pl->fast.tbl_r;
     v.n_cls = pl->fast.n_cls;
     auto *ev = pl->ds->prof_slot();
@@ -772,9 +772,13 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
     fp.ok = true;
     // sweep_packed_kernel: NDCG@k, k <= 16 ranks of 4 bits in one register per candidate
     fp.packed_ok = false;
+    fp.slots_ok = false;
     fp.len_docs.assign((size_t)pl->tb + 1, 0);
     for (uint32_t pq = 0; pq < pq_local.size(); ++pq) fp.len_docs[pq_local[pq] >> 16] += pq_local[pq] >> 16;
-    if (ndcg && fp.n_cls >= 1 && fp.n_cls <= 15 && pl->depth <= 16) {
+    const bool can_pack = ndcg && fp.n_cls >= 1 && fp.n_cls <= 15 && pl->depth <= 16;
+    // slot mode: NDCG needs the class table (<= 255 classes), AP / RR need nothing; 256-document tiles at most
+    const bool can_slot = pl->tb <= 256 && (!ndcg || fp.n_cls >= 1);
+    if (can_pack || can_slot) {
         q_order.assign(pq_local.size(), 0);
         std::vector<std::pair<uint64_t, uint16_t>> cost;
         for (uint32_t tile = 0; tile + 1 < tile_q_off.size(); ++tile) {
@@ -783,19 +787,23 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
                 const uint32_t start = pq_local[pq] & 0xffffu, len = pq_local[pq] >> 16;
                 uint64_t qcost = 64;  // fold + bookkeeping
                 uint32_t i = 0;
+                auto contributes = [&](uint32_t k) {  // 2^gain - 1 != 0 for NDCG, relevant for AP / RR
+                    const float g = ds->gain_pos[pd_pos[pq_doc0[pq] + k]];
+                    return ndcg ? g != 0.0f : g > 0.0f;
+                };
                 while (i < len) {
-                    if (ds->gain_pos[pd_pos[pq_doc0[pq] + i]] == 0.0f) {
+                    if (!contributes(i)) {
                         ++i;
                         continue;
                     }
-                    uint32_t run = 1;  // documents that can contribute: 2^gain - 1 != 0
-                    while (i + run < len && ds->gain_pos[pd_pos[pq_doc0[pq] + i + run]] != 0.0f) ++run;
+                    uint32_t run = 1;
+                    while (i + run < len && contributes(i + run)) ++run;
                     // chunks of 16 / 8 / 4: a walk of W documents costs len * (3 + 2 W) instructions
                     while (run > 0) {
                         const uint32_t n = run >= 13 ? std::min<uint32_t>(run, 16) : (run > 8 ? 8 : run);
                         const uint32_t w = n > 8 ? 16 : (n > 4 ? 8 : 4);
-                        unsigned long long tags = 0;  // gain class + 1 of each document, 4 bits apiece
-                        for (uint32_t u = 0; u < n; ++u)
+                        unsigned long long tags = 0;  // gain class + 1 of each document, 4 bits apiece (register mode)
+                        for (uint32_t u = 0; u < n && can_pack; ++u)
                             tags |= (unsigned long long)(pd_cls[pq_doc0[pq] + i + u] + 1u) << (4 * u);
                         pk_tasks.push_back(make_uint4((start + i) | (n << 16), (uint32_t)tags, (uint32_t)(tags >> 32), 0u));
                         qcost += (uint64_t)len * (3 + 2 * w) + (uint64_t)w * w;
@@ -814,17 +822,20 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
             pk_tile_off.push_back((uint32_t)pk_tasks.size());
         }
         // table with a leading row of zeros: tag 0 = nothing ranked there
-        tbl0.assign((size_t)(fp.n_cls + 1) * fp.tbl_r, 0.0);
-        for (size_t c = 0; c < cls_gain.size(); ++c) {
-            const double ge = std::pow(2.0, (double)cls_gain[c]) - 1.0;  // evaluators.rs:268
-            for (uint32_t r = 0; r < fp.tbl_r; ++r) tbl0[(c + 1) * fp.tbl_r + r] = ge / std::log2((double)r + 2.0);
+        if (ndcg) {
+            tbl0.assign((size_t)(fp.n_cls + 1) * fp.tbl_r, 0.0);
+            for (size_t c = 0; c < cls_gain.size(); ++c) {
+                const double ge = std::pow(2.0, (double)cls_gain[c]) - 1.0;  // evaluators.rs:268
+                for (uint32_t r = 0; r < fp.tbl_r; ++r) tbl0[(c + 1) * fp.tbl_r + r] = ge / std::log2((double)r + 2.0);
+            }
         }
         up.add(fp.pk_q_task_off, q_task_off);
         up.add(fp.pk_tile_task_off, pk_tile_off);
         up.add(fp.pk_tasks, pk_tasks);
         up.add(fp.pk_q_order, q_order);
-        up.add(fp.pk_tbl, tbl0);
-        fp.packed_ok = true;
+        if (!tbl0.empty()) up.add(fp.pk_tbl, tbl0);
+        fp.packed_ok = can_pack;
+        fp.slots_ok = can_slot;
     }
     CU(up.commit(pl->fast_arena, s));
     CU(cudaStreamSynchronize(s));  // the host vectors above go out of scope
@@ -837,9 +848,17 @@ extern "C" int fr_dev_plan_has_fast_sweep(const fr_dev_plan *plan) { return plan
 
 extern "C" const char *fr_dev_plan_sweep_kernel(const fr_dev_plan *plan) {
     if (!plan || !plan->fast.ok) return "";
-    bool packed = plan->fast.packed_ok;
-    if (const char *env = getenv("FASTRANK_SWEEP_KERNEL")) packed = packed && std::string(env) != "tile";
+    bool packed = plan->fast.packed_ok, slots = !packed && plan->fast.slots_ok;
+    if (const char *env = getenv("FASTRANK_SWEEP_KERNEL")) {
+        const std::string want(env);
+        if (want == "tile") packed = slots = false;
+        if (want == "slots" && plan->fast.slots_ok) {
+            packed = false;
+            slots = true;
+        }
+    }
     if (packed) return plan->tb == 128 ? "sweep_packed_kernel<128>" : plan->tb == 256 ? "sweep_packed_kernel<256>" : "sweep_packed_kernel<512>";
+    if (slots) return plan->tb == 128 ? "sweep_packed_kernel<128,slots>" : "sweep_packed_kernel<256,slots>";
     return plan->tb == 128 ? "sweep_fast_kernel<128,8>" : plan->tb == 256 ? "sweep_fast_kernel<256,8>" : "sweep_fast_kernel<512,8>";
 }
 
@@ -935,12 +954,17 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
     }
     // NDCG@k (k <= 16) takes the register-packed kernel; it tests for NaN scores only where T or
     // x_f is not finite, so candidates that are not finite themselves go to the general kernel
-    bool use_packed = fp.packed_ok;
-    for (size_t r = 0; r < n_sweeps && use_packed; ++r)
+    bool use_packed = fp.packed_ok, use_slots = !fp.packed_ok && fp.slots_ok;
+    for (size_t r = 0; r < n_sweeps && (use_packed || use_slots); ++r)
         for (uint32_t k = 0; k < n_cand[r]; ++k)
-            if (!std::isfinite(cand_w[r * cand_stride + k])) use_packed = false;
-    if (const char *env = getenv("FASTRANK_SWEEP_KERNEL")) {  // test knob: "tile" forces the general kernel
-        if (std::string(env) == "tile") use_packed = false;
+            if (!std::isfinite(cand_w[r * cand_stride + k])) use_packed = use_slots = false;
+    if (const char *env = getenv("FASTRANK_SWEEP_KERNEL")) {  // test knob: "tile" forces the general kernel,
+        const std::string want(env);                          //            "slots" the slot-buffer instance
+        if (want == "tile") use_packed = use_slots = false;
+        if (want == "slots" && fp.slots_ok && (use_packed || use_slots)) {
+            use_packed = false;
+            use_slots = true;
+        }
     }
     size_t pass = 0;
     if (!direct) CU(cudaMemsetAsync(fp.out_dev.p, 0, out_bytes, s));
@@ -1068,6 +1092,17 @@ extern "C" int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *pl, size_t n_sweeps, c
             else
                 rc = PK_LAUNCH(512, 1);
 #undef PK_LAUNCH
+        } else if (use_slots) {
+            // any measure, any cut-off: ranks filed in a per-warp slot buffer (4 CTAs per SM at 128 threads)
+            const size_t sl_bytes = PackedLayout(pl->tb, ((a.dm + 7) & ~7u) * kMaxSweeps, 0, true).total;
+            bool wsp = sl_bytes <= (pl->tb == 128 ? (size_t)55 * 1024 : (size_t)110 * 1024);
+            if (const char *env = getenv("FASTRANK_WSMEM")) wsp = atoi(env) != 0;
+            if (pl->tb == 128)
+                rc = wsp ? launch_packed<128, true, 4, 0, true>(pl, a, n_groups, s)
+                         : launch_packed<128, false, 4, 0, true>(pl, a, n_groups, s);
+            else
+                rc = wsp ? launch_packed<256, true, 2, 0, true>(pl, a, n_groups, s)
+                         : launch_packed<256, false, 2, 0, true>(pl, a, n_groups, s);
         } else if (pl->tb == 128) {
             if (ws)
                 rc = fp.td == 8 ? launch_fast<128, 8, true>(pl, a, n_groups, s)

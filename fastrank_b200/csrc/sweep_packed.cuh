@@ -51,9 +51,10 @@ struct PackedView {
 constexpr int kPruneSlots = 64;  // survivors a candidate may keep in the select-then-rank path
 
 struct PackedLayout {
-    size_t t2, sum, roww, tbl, qd, tasks, order, rowsw, misc, cls, surv, w, total;
+    size_t t2, sum, roww, tbl, qd, tasks, order, rowsw, misc, cls, surv, slots, w, total;
     // ps: survivor slots per candidate (0: the kernel instance has no select-then-rank path)
-    __host__ __device__ PackedLayout(int tb, uint32_t w_doubles, int ps) {
+    // slot_mode: ranks are filed in a per-warp shared-memory slot buffer instead of a register
+    __host__ __device__ PackedLayout(int tb, uint32_t w_doubles, int ps, bool slot_mode = false) {
         size_t o = 0;
         t2 = o;     o += sizeof(double2) * kMaxSweeps * (size_t)(tb + (ps > 0 ? 1 : 0));  // + one "never ranks" slot per row
         sum = o;    o += sizeof(unsigned long long) * kMaxRows;
@@ -66,6 +67,7 @@ struct PackedLayout {
         misc = o;   o += 256;
         cls = o;    o += align16((size_t)tb + 1);
         surv = o;   o += (tb < 256 ? 1 : 2) * (size_t)(ps ? ps + 1 : 0) * 32 * (size_t)(tb / 32);  // [warp][slot][lane], + a scratch slot
+        slots = o;  o += slot_mode ? (size_t)tb * 32 * (size_t)(tb / 32) : 0;  // [warp][rank][lane] u8
         w = o;      o += sizeof(double) * w_doubles;
         total = o;
     }
@@ -88,9 +90,12 @@ __device__ __forceinline__ unsigned long long tag_at_rank(unsigned tag, unsigned
 // Ranks the W documents [t0, t0 + n) of the query occupying tile-local [qs, qe) under this lane's
 // candidate c and files their tags by rank into `packed`: 4 bits per rank, ranks >= 16 fall off
 // the register and ranks in [lim, 16) are never read.  `tags` holds the chunk's tags, 0 beyond n.
-template <int W>
+// SLOTS: the tag (gain class + 1 for NDCG, 1 for AP / RR) goes to slot[rank][lane] of the warp's
+// shared-memory buffer instead, for ranks below lim -- any cut-off, any number of classes.
+template <int W, bool SLOTS>
 __device__ __forceinline__ void rank_chunk(const double2 *__restrict__ trow, double c, int qs, int qe, int t0, int n,
-                                           unsigned long long tags, unsigned long long &packed) {
+                                           unsigned long long tags, unsigned long long &packed, unsigned lim,
+                                           const uint8_t *__restrict__ s_cls, uint8_t *__restrict__ slot, bool class_tags) {
     double st[W];
     unsigned cnt[W];
 #pragma unroll
@@ -124,8 +129,15 @@ __device__ __forceinline__ void rank_chunk(const double2 *__restrict__ trow, dou
 #pragma unroll
         for (int i = 0; i < W; ++i) count_gt(cnt[i], sj, st[i]);
     }
+    if (SLOTS) {
 #pragma unroll
-    for (int i = 0; i < W; ++i) packed |= tag_at_rank((unsigned)(tags >> (4 * i)) & 15u, cnt[i]);
+        for (int i = 0; i < W; ++i) {
+            if (i < n && cnt[i] < lim) slot[cnt[i] * 32] = class_tags ? (uint8_t)(s_cls[t0 + i] + 1) : (uint8_t)1;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) packed |= tag_at_rank((unsigned)(tags >> (4 * i)) & 15u, cnt[i]);
+    }
 }
 
 // Select-then-rank for long lists (NDCG@k, k << len).  Per candidate (lane):
@@ -272,7 +284,7 @@ __device__ __forceinline__ bool rank_pruned(const double2 *__restrict__ trow, do
     return true;
 }
 
-template <int TB, bool WS, int MINB, int PS>
+template <int TB, bool WS, int MINB, int PS, bool SLOTS>
 __global__ void __launch_bounds__(TB, MINB)
 sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -285,7 +297,7 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
     const int R = (int)(A.grp_row_off[blockIdx.y + 1] - row0);  // rows of this sweep group
     const int G = (R + 31) >> 5;
     const uint32_t dm8 = (dm + 7) & ~7u;
-    const PackedLayout L(TB, WS ? dm8 * NS : 0u, PS);
+    const PackedLayout L(TB, WS ? dm8 * NS : 0u, PS, SLOTS);
     double2 *s_t2 = (double2 *)(smem_raw + L.t2);  // [NS][TB + 1]
     constexpr int T2S = PS > 0 ? TB + 1 : TB;     // slot TB of every row: a document that never ranks
     uint8_t *s_cls = (uint8_t *)(smem_raw + L.cls);
@@ -302,6 +314,9 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
     const double *__restrict__ wg = A.base_wt + (size_t)blockIdx.y * dm8 * NS;
     double *s_w = (double *)(smem_raw + L.w);
     const uint32_t tbl_r = V.tbl_r;
+    uint8_t *s_slot = (uint8_t *)(smem_raw + L.slots) + (size_t)(t >> 5) * TB * 32 + lane;  // [rank][lane] of this warp
+    const bool tbl_smem = (V.n_cls + 1) * tbl_r <= 256u;
+    const double *tbl = tbl_smem ? s_tbl : V.tbl;
 
     // ---- per-launch setup ----
     for (int idx = t; idx < kMaxRows; idx += TB) {
@@ -309,7 +324,8 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
         s_roww[idx] = idx < R ? A.row_w[row0 + idx] : 0.0;
         s_sum[idx] = 0ull;
     }
-    for (uint32_t idx = t; idx < (V.n_cls + 1) * tbl_r; idx += TB) s_tbl[idx] = V.tbl[idx];
+    if (tbl_smem && V.tbl != nullptr)
+        for (uint32_t idx = t; idx < (V.n_cls + 1) * tbl_r; idx += TB) s_tbl[idx] = V.tbl[idx];
     if (PS > 0) {
         if (t < NS) s_t2[(size_t)t * T2S + TB] = make_double2(__longlong_as_double(0xfff0000000000000ll), 0.0);
         if (t == 0) s_cls[TB] = (uint8_t)255;  // tag (255 + 1) & 15 = 0: files nothing
@@ -356,7 +372,7 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
         const uint32_t q0 = P.tile_q_off[tile];
         const int nqt = (int)(P.tile_q_off[tile + 1] - q0);
         if (t < ntask) s_tasks[t] = V.tasks[task0 + t];
-        if (PS > 0) s_cls[t] = active ? __ldg(V.pd_cls + doc0 + t) : (uint8_t)255;
+        if (PS > 0 || SLOTS) s_cls[t] = active ? __ldg(V.pd_cls + doc0 + t) : (uint8_t)255;
         if (t < nqt) {
             const uint32_t tb0 = V.q_task_off[q0 + t], tb1 = V.q_task_off[q0 + t + 1];
             s_qd[t] = make_uint2(P.pq_local[q0 + t], (tb0 - task0) | ((tb1 - tb0) << 16));
@@ -443,7 +459,8 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
             const uint2 qd = s_qd[ql];
             const int qs = (int)(qd.x & 0xffffu), len = (int)(qd.x >> 16), qe = qs + len;
             const int tk0 = (int)(qd.y & 0xffffu), ntk = (int)(qd.y >> 16);
-            const unsigned lim = (unsigned)P.depth < (unsigned)len ? (unsigned)P.depth : (unsigned)len;
+            const unsigned lim = (P.metric == FR_METRIC_NDCG && (unsigned)P.depth < (unsigned)len) ? (unsigned)P.depth
+                                                                                                : (unsigned)len;
             const int row = (g << 5) + lane;
             const bool live = row < R;
             const int rowc = live ? row : R - 1;
@@ -454,30 +471,55 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
             if (PS > 0 && A.prune_min > 0 && len >= (int)A.prune_min && ntk > 0)
                 ranked = rank_pruned<TB, (PS > 0 ? PS : 8)>(trow, c, qs, qe, lim, s_cls, s_surv, lane, packed);
             if (!ranked) packed = 0ull;
+            if (SLOTS) {  // clear the ranks this list can reach (lane-private column of the warp's buffer)
+                for (unsigned r = 0; r < lim; ++r) s_slot[r * 32] = (uint8_t)0;
+            }
+            const bool class_tags = P.metric == FR_METRIC_NDCG;
             for (int tk = tk0; tk < tk0 + (ranked ? 0 : ntk); ++tk) {
                 const uint4 w = s_tasks[tk];
                 const int t0 = (int)(w.x & 0xffffu), n = (int)(w.x >> 16);
                 const unsigned long long tags = (unsigned long long)w.y | ((unsigned long long)w.z << 32);
                 if (n > 8)
-                    rank_chunk<16>(trow, c, qs, qe, t0, n, tags, packed);
+                    rank_chunk<16, SLOTS>(trow, c, qs, qe, t0, n, tags, packed, lim, s_cls, s_slot, class_tags);
                 else if (n > 4 || PK_NO_W4)
-                    rank_chunk<8>(trow, c, qs, qe, t0, n, tags, packed);
+                    rank_chunk<8, SLOTS>(trow, c, qs, qe, t0, n, tags, packed, lim, s_cls, s_slot, class_tags);
                 else
-                    rank_chunk<4>(trow, c, qs, qe, t0, n, tags, packed);
+                    rank_chunk<4, SLOTS>(trow, c, qs, qe, t0, n, tags, packed, lim, s_cls, s_slot, class_tags);
             }
             // fold: ranks 0 .. lim-1 in order (evaluators.rs:265-270); an empty slot adds +0.0 like a
             // zero-gain document does in the reference
             const uint32_t pq = q0 + ql;
             const double norm = P.pq_norm[pq];
             double value = 0.0;
-            if (norm == norm) {  // Some(ideal), evaluators.rs:351-358
-                double dcg = 0.0;
-                for (unsigned r = 0; r < lim; ++r) {
-                    const unsigned tag = (unsigned)(packed >> (r << 2)) & 15u;
-                    dcg = __dadd_rn(dcg, s_tbl[tag * tbl_r + r]);
+            if (!SLOTS || P.metric == FR_METRIC_NDCG) {
+                if (norm == norm) {  // Some(ideal), evaluators.rs:351-358
+                    double dcg = 0.0;
+                    for (unsigned r = 0; r < lim; ++r) {
+                        const unsigned tag = SLOTS ? (unsigned)s_slot[r * 32] : (unsigned)(packed >> (r << 2)) & 15u;
+                        dcg = __dadd_rn(dcg, tbl[tag * tbl_r + r]);
+                    }
+                    if (dcg > norm) atomicOr(A.err, ERR_DCG_ABOVE_IDEAL);
+                    value = dcg / norm;
                 }
-                if (dcg > norm) atomicOr(A.err, ERR_DCG_ABOVE_IDEAL);
-                value = dcg / norm;
+            } else if (P.metric == FR_METRIC_AP) {  // evaluators.rs:418-448
+                if (norm > 0.0) {
+                    unsigned recall = 0;
+                    double sum = 0.0;
+                    for (unsigned r = 0; r < lim; ++r) {
+                        if (s_slot[r * 32]) {
+                            recall += 1;
+                            sum = __dadd_rn(sum, (double)recall / (double)(r + 1));
+                        }
+                    }
+                    value = sum / norm;
+                }
+            } else {  // evaluators.rs:235-253
+                for (unsigned r = 0; r < lim; ++r) {
+                    if (s_slot[r * 32]) {
+                        value = 1.0 / (double)(r + 1);
+                        break;
+                    }
+                }
             }
             if (live) {
                 if (A.perq) A.perq[(size_t)A.row_out[row0 + row] * P.nq_view + P.pq_view[pq]] = value;

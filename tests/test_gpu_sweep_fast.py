@@ -434,3 +434,44 @@ def test_packed_kernel_equals_general_kernel_bit_for_bit(oracle, monkeypatch, de
             assert abs(got[None][1][r, k].mean() - exp.mean()) < 1e-9
     finally:
         dev.close()
+
+
+@pytest.mark.parametrize("name,metric,depth", [("ndcg", 0, -1), ("ndcg@20", 0, 20), ("map", 1, -1), ("rr", 2, -1), ("ndcg@10", 0, 10)])
+def test_slot_mode_of_the_packed_kernel_equals_general_kernel(oracle, monkeypatch, name, metric, depth):
+    """Measures the register-packed top-k cannot hold (NDCG without cut-off or k > 16, AP, RR) run the
+    same warp-item kernel with ranks filed in a per-warp slot buffer (tiles of <= 256 documents).
+    FASTRANK_SWEEP_KERNEL=tile forces the general tile kernel, =slots forces slot mode where the
+    register mode would apply: same bits everywhere, and the oracle's on exact arithmetic."""
+    rng = np.random.default_rng(190 + metric + depth)
+    lens = [int(v) for v in rng.integers(1, 70, 300)] + [130, 255, 1, 2, 33, 256]
+    X, y, qid = _ragged(rng, lens, d=16)
+    y[rng.random(len(y)) < 0.05] = -1.0
+    y[qid == 5] = 0.0
+    _, _, _, ods, dev = _mk(oracle, 0, 0, 0, 0, X=X, y=y, qid=qid)
+    base = rng.normal(size=(8, 16))
+    base /= np.abs(base).sum(axis=1, keepdims=True)
+    fids = [int(v) for v in rng.integers(0, 16, 8)]
+    cands = [_line(base[r, fids[r]], 51) for r in range(8)]
+    got = {}
+    try:
+        plan = dev.plan(metric, depth)
+        assert dev.lib.fr_dev_plan_tile_documents(plan.ptr) == 256
+        for which in ("tile", "slots", None):
+            if which is None:
+                monkeypatch.delenv("FASTRANK_SWEEP_KERNEL", raising=False)
+            else:
+                monkeypatch.setenv("FASTRANK_SWEEP_KERNEL", which)
+            kernel = dev.ffi.string(dev.lib.fr_dev_plan_sweep_kernel(plan.ptr)).decode()
+            got[which] = plan.coord_sweeps(base, fids, cands, fast=True, per_query=True) + (kernel,)
+        assert got["tile"][2].startswith("sweep_fast_kernel") and got["slots"][2].endswith("slots>")
+        assert got[None][2].endswith("slots>") == (name != "ndcg@10")
+        for which in ("slots", None):
+            assert np.array_equal(got["tile"][0], got[which][0]), which
+            assert np.array_equal(got["tile"][1], got[which][1]), which
+        for r, k in ((0, 0), (5, 33)):
+            w = base[r].copy()
+            w[fids[r]] = cands[r][k]
+            exp = oracle.evaluate_scores(ods, oracle.score_linear(X, w), name)
+            assert abs(got[None][1][r, k].mean() - exp.mean()) < 1e-9
+    finally:
+        dev.close()

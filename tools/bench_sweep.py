@@ -26,7 +26,7 @@ def main():
     X, y, qid = bench.make_data(n, 136, q)
     qidx, nq = dense_query_index(qid)
     dev = DevDataset(X, y.astype(np.float32), qidx, nq)
-    plan = dev.plan(0, int(os.environ.get("DEPTH", 10)))
+    plan = dev.plan(int(os.environ.get("METRIC", 0)), int(os.environ.get("DEPTH", 10)))  # 0 NDCG, 1 AP, 2 RR; depth -1 = none
     packed = []
     n_sw = int(os.environ.get("SWEEPS", 8))  # restarts per launch (2-D sharding experiments: 4 or 2)
     for s in range(steps + 3):
