@@ -226,8 +226,9 @@ int fr_dev_eval_coord_sweeps_fast(fr_dev_plan *plan, size_t n_sweeps, const doub
 int fr_dev_plan_has_fast_sweep(const fr_dev_plan *plan);
 /* Name of the kernel that serves fr_dev_eval_coord_sweeps_fast on this plan (static string):
  * "sweep_packed_kernel<TILE>" for NDCG@k with k <= 16 and at most 15 gain classes (a candidate's
- * top-k kept in one 64-bit register), "sweep_fast_kernel<TILE,8>" otherwise, "" when the plan
- * has no batched sweep.  For reports (bench.py roofline.kernel). */
+ * top-k kept in one 64-bit register), "sweep_packed_kernel<TILE,slots>" for the other measures on
+ * tiles of up to 256 documents (ranks filed in a per-warp slot buffer), "sweep_fast_kernel<TILE,8>"
+ * otherwise, "" when the plan has no batched sweep.  For reports (bench.py roofline.kernel). */
 const char *fr_dev_plan_sweep_kernel(const fr_dev_plan *plan);
 
 /* Bootstrap resampling of per-query values (evaluators.rs:157-171): `trials` means of n_values
