@@ -1,3 +1,6 @@
+#!/bin/bash
+# Re-creates the evidence under profiles/ on a B200 box:  gpurun --timeout 1800 -- bash tools/capture_profiles.sh
+# (outputs land in gpurun_out/cap/; summarise with tools/ncu_summary.py / ncu_lines.py / launch_summary.py)
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out/cap
 # 1. launch list of the bench command (short)
@@ -7,6 +10,9 @@ ncu --set full --clock-control none --import-source on -k regex:sweep_packed -s 
 # 3. MSLR-shaped launch
 N=3771125 Q=31531 STEPS=1 ncu --set full --clock-control none --import-source on -k regex:sweep_packed -s 2 -c 1 -o gpurun_out/cap/r02_sweep_packed_mslr python tools/bench_sweep.py "" > gpurun_out/cap/ncu_mslr.log 2>&1
 # 4. micro-benchmarks
+for m in cmp_throughput:cmp read_pattern:read_pattern; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/micro/${m#*:} tools/micro/${m%:*}.cu
+done
 ./tools/micro/cmp > gpurun_out/cap/r02_micro_compare_throughput.txt 2>&1
 ./tools/micro/read_pattern > gpurun_out/cap/r02_micro_read_pattern.txt 2>&1
 # 5. evaluate bench, both load paths
