@@ -346,6 +346,8 @@ struct FastPlan {
     DevBuf<uint4> pk_tasks;             // chunks of <= 16 documents, grouped by query (PackedView::tasks)
     DevBuf<uint16_t> pk_q_order;        // tile-local query indices, costliest first
     DevBuf<double> pk_tbl;              // [n_cls + 1][tbl_r], row 0 zeros
+    DevBuf<double> ap_tbl;              // AP: [relevant so far][rank] -> precision, the fold's divisions done once
+    uint32_t ap_cols = 0;
     // per-call work buffers (sweep_fast.cu documents the layout): one input blob = transposed
     // weights + the call's candidates flattened into rows, one output blob = sums, error flags,
     // tile counters; each moves with a single copy through pinned memory

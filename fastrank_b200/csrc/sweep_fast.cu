@@ -650,6 +650,8 @@ int launch_packed(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStr
     v.tasks = pl->fast.pk_tasks.p;
     v.pd_cls = pl->fast.pd_cls.p;
     v.tbl = pl->fast.pk_tbl.n ? pl->fast.pk_tbl.p : nullptr;
+    v.ap_tbl = pl->fast.ap_tbl.n ? pl->fast.ap_tbl.p : nullptr;
+    v.ap_cols = pl->fast.ap_cols;
     v.tbl_r = pl->fast.tbl_r;
     v.n_cls = pl->fast.n_cls;
     auto *ev = pl->ds->prof_slot();
@@ -709,7 +711,7 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
     }
     cudaStream_t s = ds->stream;
     UploadBatch up;  // every array of the sweep plan in one allocation
-    std::vector<double> tbl_host, tbl0;
+    std::vector<double> tbl_host, tbl0, ap_host;
     std::vector<uint32_t> q_task_off{0}, pk_tile_off{0};
     std::vector<uint4> pk_tasks;
     std::vector<uint16_t> q_order;
@@ -834,6 +836,24 @@ int build_fast_plan(fr_dev_plan *pl, const std::vector<uint32_t> &tile_q_off,
         up.add(fp.pk_tasks, pk_tasks);
         up.add(fp.pk_q_order, q_order);
         if (!tbl0.empty()) up.add(fp.pk_tbl, tbl0);
+        if (pl->metric == FR_METRIC_AP && can_slot) {
+            // precision table: recall / (rank + 1) for every (relevant documents so far, rank) the plan's
+            // lists can produce -- the same IEEE divisions the reference performs (evaluators.rs:440-444)
+            uint32_t max_rel = 0;
+            for (uint32_t pq = 0; pq < pq_local.size(); ++pq) {
+                uint32_t rel = 0;
+                for (uint32_t k = 0; k < (pq_local[pq] >> 16); ++k) rel += ds->gain_pos[pd_pos[pq_doc0[pq] + k]] > 0.0f;
+                max_rel = std::max(max_rel, rel);
+            }
+            const size_t cols = std::max<uint32_t>(pl->max_len, 1), rows = (size_t)max_rel + 1;
+            if (rows * cols <= ((size_t)1 << 19)) {  // <= 4 MB
+                ap_host.assign(rows * cols, 0.0);
+                for (size_t rc = 1; rc < rows; ++rc)
+                    for (size_t r = 0; r < cols; ++r) ap_host[rc * cols + r] = (double)rc / (double)(r + 1);
+                fp.ap_cols = (uint32_t)cols;
+                up.add(fp.ap_tbl, ap_host);
+            }
+        }
         fp.packed_ok = can_pack;
         fp.slots_ok = can_slot;
     }

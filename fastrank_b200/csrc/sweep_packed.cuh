@@ -46,6 +46,8 @@ struct PackedView {
     const uint8_t *pd_cls;          // plan doc -> gain class (select-then-rank path)
     const double *tbl;              // [n_cls + 1][tbl_r]: row 0 zeros (empty slot), row c + 1 = class c
     uint32_t tbl_r, n_cls;
+    const double *ap_tbl;           // AP: [recall][rank] = (double)recall / (double)(rank + 1), or nullptr
+    uint32_t ap_cols;               // ranks per row of ap_tbl
 };
 
 constexpr int kPruneSlots = 64;  // survivors a candidate may keep in the select-then-rank path
@@ -505,10 +507,15 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
                 if (norm > 0.0) {
                     unsigned recall = 0;
                     double sum = 0.0;
+                    // precision at each relevant rank: the quotients come from a host-built table of
+                    // the same IEEE divisions when the plan has one (an f64 divide is ~40 instructions)
+                    const double *__restrict__ apt = V.ap_tbl;
                     for (unsigned r = 0; r < lim; ++r) {
                         if (s_slot[r * 32]) {
                             recall += 1;
-                            sum = __dadd_rn(sum, (double)recall / (double)(r + 1));
+                            const double prec = apt ? __ldg(apt + (size_t)recall * V.ap_cols + r)
+                                                    : (double)recall / (double)(r + 1);
+                            sum = __dadd_rn(sum, prec);
                         }
                     }
                     value = sum / norm;
