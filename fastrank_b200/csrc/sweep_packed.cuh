@@ -317,8 +317,9 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
     double *s_w = (double *)(smem_raw + L.w);
     const uint32_t tbl_r = V.tbl_r;
     uint8_t *s_slot = (uint8_t *)(smem_raw + L.slots) + (size_t)(t >> 5) * TB * 32 + lane;  // [rank][lane] of this warp
-    const bool tbl_smem = (V.n_cls + 1) * tbl_r <= 256u;
-    const double *tbl = tbl_smem ? s_tbl : V.tbl;
+    // the register mode's table always fits shared memory (<= 16 classes x 16 ranks); slot mode may
+    // have to read a larger one through L1
+    const bool tbl_smem = !SLOTS || (V.n_cls + 1) * tbl_r <= 256u;
 
     // ---- per-launch setup ----
     for (int idx = t; idx < kMaxRows; idx += TB) {
@@ -498,7 +499,8 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
                     double dcg = 0.0;
                     for (unsigned r = 0; r < lim; ++r) {
                         const unsigned tag = SLOTS ? (unsigned)s_slot[r * 32] : (unsigned)(packed >> (r << 2)) & 15u;
-                        dcg = __dadd_rn(dcg, tbl[tag * tbl_r + r]);
+                        const double term = (!SLOTS || tbl_smem) ? s_tbl[tag * tbl_r + r] : __ldg(V.tbl + tag * tbl_r + r);
+                        dcg = __dadd_rn(dcg, term);
                     }
                     if (dcg > norm) atomicOr(A.err, ERR_DCG_ABOVE_IDEAL);
                     value = dcg / norm;
