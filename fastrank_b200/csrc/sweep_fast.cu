@@ -642,6 +642,7 @@ int launch_packed(fr_dev_plan *pl, const FastArgs &a, uint32_t n_groups, cudaStr
         const int div = atoi(env);
         args.n_split = div > 0 ? gx / (uint32_t)div : (div < 0 ? pl->nt : 0u);
     }
+    if (const char *env = getenv("FASTRANK_NSPLIT")) args.n_split = (uint32_t)std::min<long>(std::max<long>(atol(env), 0), pl->nt);
     if (const char *env = getenv("FASTRANK_SPLIT_PARTS")) args.split_parts = atoi(env) == 2 ? 2u : 4u;
     PackedView v;
     v.q_task_off = pl->fast.pk_q_task_off.p;

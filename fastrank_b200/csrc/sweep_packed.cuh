@@ -474,11 +474,40 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
             if (PS > 0 && A.prune_min > 0 && len >= (int)A.prune_min && ntk > 0)
                 ranked = rank_pruned<TB, (PS > 0 ? PS : 8)>(trow, c, qs, qe, lim, s_cls, s_surv, lane, packed);
             if (!ranked) packed = 0ull;
-            if (SLOTS) {  // clear the ranks this list can reach (lane-private column of the warp's buffer)
+            // RR needs one rank only, the best relevant document's: the relevant document with the
+            // highest score (the earliest of equals -- list order breaks ties), then one count of
+            // the documents that outrank it.  O(len) per candidate instead of relevant x len.
+            const bool first_rank_only = SLOTS && P.metric == FR_METRIC_RR;
+            double value = 0.0;
+            if (first_rank_only && ntk > 0) {
+                int bi = -1;
+                double best = 0.0;
+                for (int tk = tk0; tk < tk0 + ntk; ++tk) {
+                    const unsigned wx = s_tasks[tk].x;
+                    const int t0 = (int)(wx & 0xffffu), n = (int)(wx >> 16);
+                    for (int i = t0; i < t0 + n; ++i) {
+                        const double2 tx = trow[i];
+                        const double si = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+                        if (bi < 0 || si > best) {
+                            best = si;
+                            bi = i;
+                        }
+                    }
+                }
+                unsigned above = 0;
+#pragma unroll 4
+                for (int jq = qs; jq < qe; ++jq) {
+                    const double2 tx = trow[jq];
+                    const double sj = __dadd_rn(tx.x, __dmul_rn(tx.y, c));
+                    above += (jq < bi ? sj >= best : sj > best) ? 1u : 0u;
+                }
+                value = 1.0 / (double)(above + 1u);  // evaluators.rs:235-253
+            }
+            if (SLOTS && !first_rank_only) {  // clear the ranks this list can reach (lane-private column of the warp's buffer)
                 for (unsigned r = 0; r < lim; ++r) s_slot[r * 32] = (uint8_t)0;
             }
             const bool class_tags = P.metric == FR_METRIC_NDCG;
-            for (int tk = tk0; tk < tk0 + (ranked ? 0 : ntk); ++tk) {
+            for (int tk = tk0; tk < tk0 + ((ranked || first_rank_only) ? 0 : ntk); ++tk) {
                 const uint4 w = s_tasks[tk];
                 const int t0 = (int)(w.x & 0xffffu), n = (int)(w.x >> 16);
                 const unsigned long long tags = (unsigned long long)w.y | ((unsigned long long)w.z << 32);
@@ -493,8 +522,9 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
             // zero-gain document does in the reference
             const uint32_t pq = q0 + ql;
             const double norm = P.pq_norm[pq];
-            double value = 0.0;
-            if (!SLOTS || P.metric == FR_METRIC_NDCG) {
+            if (first_rank_only) {
+                // value set above
+            } else if (!SLOTS || P.metric == FR_METRIC_NDCG) {
                 if (norm == norm) {  // Some(ideal), evaluators.rs:351-358
                     double dcg = 0.0;
                     for (unsigned r = 0; r < lim; ++r) {
@@ -521,13 +551,6 @@ sweep_packed_kernel(PlanView P, PackedView V, FastArgs A) {
                         }
                     }
                     value = sum / norm;
-                }
-            } else {  // evaluators.rs:235-253
-                for (unsigned r = 0; r < lim; ++r) {
-                    if (s_slot[r * 32]) {
-                        value = 1.0 / (double)(r + 1);
-                        break;
-                    }
                 }
             }
             if (live) {

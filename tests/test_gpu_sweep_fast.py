@@ -475,3 +475,32 @@ def test_slot_mode_of_the_packed_kernel_equals_general_kernel(oracle, monkeypatc
             assert abs(got[None][1][r, k].mean() - exp.mean()) < 1e-9
     finally:
         dev.close()
+
+
+@pytest.mark.parametrize("name,metric", [("mrr", 2), ("map", 1), ("ndcg", 0)])
+def test_slot_mode_with_many_tied_scores_is_bit_identical_to_the_oracle(oracle, monkeypatch, name, metric):
+    """Small-integer features and dyadic weights: scores are exact and tie all the time, so the tie
+    rule decides most ranks -- in particular which relevant document is "the first" for RR, whose
+    slot-mode path finds the best relevant document and counts once instead of ranking them all.
+    Tiles of <= 256 documents (slot mode), compared with the general kernel and with the oracle."""
+    rng = np.random.default_rng(300 + metric)
+    lens = [int(v) for v in rng.integers(1, 60, 250)] + [200, 256, 1, 2]
+    X, y, qid = _ragged(rng, lens, d=6, integer=True)
+    y[qid == 3] = 0.0          # a list without relevant documents
+    y[qid == 5] = 2.0          # and one with nothing else
+    _, _, _, ods, dev = _mk(oracle, 0, 0, 0, 0, X=X, y=y, qid=qid)
+    base = rng.integers(-4, 5, size=(3, 6)).astype(np.float64) / 8.0
+    cands = [[float(v) / 4.0 for v in rng.integers(-8, 9, 40)] for _ in range(3)]
+    try:
+        plan = dev.plan(metric, -1)
+        assert dev.lib.fr_dev_plan_tile_documents(plan.ptr) == 256
+        monkeypatch.delenv("FASTRANK_SWEEP_KERNEL", raising=False)
+        assert dev.ffi.string(dev.lib.fr_dev_plan_sweep_kernel(plan.ptr)).decode().endswith("slots>")
+        got = plan.coord_sweeps(base, [0, 2, 5], cands, fast=True, per_query=True)
+        monkeypatch.setenv("FASTRANK_SWEEP_KERNEL", "tile")
+        ref = plan.coord_sweeps(base, [0, 2, 5], cands, fast=True, per_query=True)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+        monkeypatch.delenv("FASTRANK_SWEEP_KERNEL", raising=False)
+        _check(oracle, ods, X, plan, name, base, [0, 2, 5], cands, exact=True)
+    finally:
+        dev.close()
