@@ -207,9 +207,28 @@ fr_dev_dataset *ParentDataset::device() {
         if (fr_dev_dataset_create(which, n, d, x, gains.data(), query_of.data(),
                                   (uint32_t)query_names.size(), &out))
             throw Error(std::string("GPU dataset upload failed: ") + fr_dev_last_error());
-        // libsvm data: which leading feature ids each (Dense32) row carries; Sparse32 rows are not
-        // described this way (random-forest statistics for such data stay on the host)
-        if (!dense_source && sparse_ids.empty() && row_len.size() == n) {
+        // libsvm data: which feature ids each row carries -- a bitmap when some rows are Sparse32
+        // (the listed ids), else the rows' lengths (Dense32: the leading ids)
+        if (!dense_source && !sparse_ids.empty() && row_len.size() == n) {
+            const uint32_t words = (uint32_t)((d + 31) / 32);
+            std::vector<uint32_t> bits(n * (size_t)words, 0u);
+            for (size_t i = 0; i < n; ++i) {
+                uint32_t *row = bits.data() + i * words;
+                if (row_len[i] > 0) {
+                    for (uint32_t f = 0; f < row_len[i] && f < d; ++f) row[f >> 5] |= 1u << (f & 31u);
+                } else {
+                    auto it = sparse_ids.find((uint32_t)i);
+                    if (it != sparse_ids.end())
+                        for (uint32_t f : it->second)
+                            if (f < d) row[f >> 5] |= 1u << (f & 31u);
+                }
+            }
+            if (fr_dev_dataset_set_row_presence(out, bits.data(), words)) {
+                const std::string why = fr_dev_last_error();
+                fr_dev_dataset_destroy(out);
+                throw Error("GPU dataset upload failed: " + why);
+            }
+        } else if (!dense_source && row_len.size() == n) {
             bool ragged = false;
             for (uint32_t len : row_len) ragged |= len < d;
             if (ragged && fr_dev_dataset_set_row_lengths(out, row_len.data())) {

@@ -1122,6 +1122,19 @@ int fr_dev_dataset_set_row_lengths(fr_dev_dataset *ds, const uint32_t *row_len) 
     return 0;
 }
 
+int fr_dev_dataset_set_row_presence(fr_dev_dataset *ds, const uint32_t *bits, uint32_t words_per_row) {
+    if (!ds || !bits) return fail("fr_dev_dataset_set_row_presence: NULL argument");
+    if ((size_t)words_per_row * 32 < ds->d) return fail("fr_dev_dataset_set_row_presence: fewer bits than features");
+    CU(cudaSetDevice(ds->device));
+    std::vector<uint32_t> by_pos(ds->n * (size_t)words_per_row);
+    for (size_t p = 0; p < ds->n; ++p)
+        memcpy(by_pos.data() + p * words_per_row, bits + (size_t)ds->inst_of_pos[p] * words_per_row, 4 * (size_t)words_per_row);
+    CU(ds->present_pos.upload(by_pos, ds->stream));
+    CU(cudaStreamSynchronize(ds->stream));
+    ds->present_words = words_per_row;
+    return 0;
+}
+
 void fr_dev_dataset_destroy(fr_dev_dataset *ds) {
     if (!ds) return;
     cudaSetDevice(ds->device);

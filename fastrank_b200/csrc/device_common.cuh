@@ -253,6 +253,8 @@ struct fr_dev_dataset {
     DevBuf<double> gexp;    // [n] by position
     DevBuf<uint32_t> inst_of_pos_dev;
     DevBuf<uint32_t> len_pos;    // optional, by position: features below this id are present in the row (libsvm data)
+    DevBuf<uint32_t> present_pos;  // optional, by position: bitmap of the feature ids the row carries (Sparse32 rows)
+    uint32_t present_words = 0;    // 32-bit words per row of present_pos
     std::vector<uint32_t> inst_of_pos, pos_of_inst;
     std::vector<uint32_t> q_start, q_len;  // per query, in positions
     std::vector<float> gain_pos;           // host copy, by position

@@ -487,11 +487,11 @@ Model random_forest_learn(const RandomForestParams &p, const DatasetView &view, 
     });
     if (all_features.empty()) throw Error("dataset has no features");
 
-    // Where do the per-level statistics come from?  The device path takes from_numpy data and
-    // libsvm data whose rows are all Dense32 (a row's missing features are then "ids beyond its
-    // length", which the device knows through fr_dev_dataset_set_row_lengths); it needs labels that
-    // are exact in its integer unit; FASTRANK_RF=host / gpu overrides the size heuristic.
-    const bool device_capable = parent.dense_source || parent.sparse_ids.empty();
+    // Where do the per-level statistics come from?  The device knows which features a libsvm row
+    // carries (fr_dev_dataset_set_row_lengths for Dense32 rows, _set_row_presence when some rows
+    // are Sparse32); it needs labels that are exact in its integer unit; FASTRANK_RF=host / gpu
+    // overrides the size heuristic.
+    const bool device_capable = true;
     bool on_device = device_capable && view.num_instances() >= 50000;
     if (const char *env = getenv("FASTRANK_RF")) {
         if (std::string(env) == "host") on_device = false;

@@ -32,7 +32,9 @@ struct RfLevel {
     size_t ld;
     const float *gain;        // by position
     const uint32_t *len_pos;  // nullptr, or by position: feature ids >= len_pos[p] are missing in that row
-    unsigned *f_present;      // [n_active][F] instances that carry the feature (written when len_pos is set)
+    const uint32_t *present_bits;  // nullptr, or by position: present_words words, bit f = the row carries feature f
+    uint32_t present_words;
+    unsigned *f_present;      // [n_active][F] instances that carry the feature (written when rows can miss features)
     const uint32_t *samp_pos; // [m] position of every sampled instance
     const int *node_of;       // [m] active node of the instance, -1 = settled in a leaf
     uint32_t m;
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(kRfThreads) rf_minmax_kernel(RfLevel L) {
     unsigned *scnt = (unsigned *)(sgmx + L.n_active);
     long long *ssum = (long long *)(scnt + L.n_active + (L.n_active & 1));
     unsigned *sfp = (unsigned *)(ssum + L.n_active);  // instances of the node that carry this feature
-    const bool sparse = L.len_pos != nullptr;
+    const bool sparse = L.len_pos != nullptr || L.present_bits != nullptr;
     const uint32_t fid = L.feats[f];
     for (uint32_t a = threadIdx.x; a < L.n_active; a += blockDim.x) {
         smn[a] = INT_MAX;
@@ -82,7 +84,11 @@ __global__ void __launch_bounds__(kRfThreads) rf_minmax_kernel(RfLevel L) {
         if (uniform && nid < 0) continue;
         const uint32_t p = nid >= 0 ? L.samp_pos[i] : 0u;
         // normalizers.rs:21-27: a row that does not carry the feature is left out of its min / max
-        const bool present = nid >= 0 && (!sparse || fid < __ldg(L.len_pos + p));
+        bool present = nid >= 0;
+        if (present && L.present_bits)
+            present = (__ldg(L.present_bits + (size_t)p * L.present_words + (fid >> 5)) >> (fid & 31u)) & 1u;
+        else if (present && L.len_pos)
+            present = fid < __ldg(L.len_pos + p);
         const int o = nid >= 0 ? ford(__ldg(row + p)) : 0;
         const float g = (labels && nid >= 0) ? __ldg(L.gain + p) : 0.f;
         const int og = ford(g);
@@ -346,6 +352,8 @@ int fr_dev_rf_level_stats(fr_dev_rf *rf, uint32_t n_active, uint32_t k, uint64_t
     L.ld = ds->ld;
     L.gain = ds->gain.p;
     L.len_pos = ds->len_pos.n ? ds->len_pos.p : nullptr;
+    L.present_bits = ds->present_pos.n ? ds->present_pos.p : nullptr;
+    L.present_words = ds->present_words;
     L.f_present = (unsigned *)(b + o_fp);
     L.samp_pos = rf->samp_pos.p;
     L.node_of = rf->node_of.p;
@@ -395,7 +403,7 @@ int fr_dev_rf_level_stats(fr_dev_rf *rf, uint32_t n_active, uint32_t k, uint64_t
     memcpy(b_n, host.data() + o_bn, 4 * cells);
     memcpy(b_pos, host.data() + o_bpos, 4 * cells);
     if (f_present) {
-        if (L.len_pos) {
+        if (L.len_pos || L.present_bits) {
             memcpy(f_present, host.data() + o_fp, 4 * nf);
         } else {  // nothing is missing: every instance of the node carries every feature
             for (size_t i = 0; i < nf; ++i) f_present[i] = (uint32_t)node_n[i / rf->F];

@@ -154,6 +154,10 @@ int fr_dev_dataset_create(int device, size_t n, size_t d, const float *x, const 
  * random_forest.rs:228) but are skipped by FeatureStats (normalizers.rs:21-27), which is what the
  * random-forest statistics below honour.  Without this call nothing is missing. */
 int fr_dev_dataset_set_row_lengths(fr_dev_dataset *ds, const uint32_t *row_len);
+/* The same for data with Sparse32 rows (instance.rs:118-121: a row that lists fewer than half of the
+ * ids up to its largest carries exactly the listed ones): bits[i * words_per_row + (f >> 5)] bit
+ * (f & 31) = instance i carries feature f.  Takes precedence over the row lengths. */
+int fr_dev_dataset_set_row_presence(fr_dev_dataset *ds, const uint32_t *bits, uint32_t words_per_row);
 void fr_dev_dataset_destroy(fr_dev_dataset *ds);
 size_t fr_dev_dataset_bytes(const fr_dev_dataset *ds); /* HBM footprint */
 

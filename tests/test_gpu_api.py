@@ -704,6 +704,53 @@ def test_random_forest_golden_with_missing_features_on_either_path(fr, goldens, 
     assert "%.3g" % np.mean(list(test_ds.evaluate(rf, "NDCG@5").values())) == g["test_ndcg5_printed"]
 
 
+def test_random_forest_on_sparse_rows_same_forest_on_host_gpu_and_oracle(fr, oracle, tmp_path, monkeypatch):
+    """libsvm rows that list fewer than half of the ids up to their largest are Sparse32
+    (instance.rs:118-121): exactly the listed features are present.  The device learns that through
+    a per-row bitmap (fr_dev_dataset_set_row_presence), so the per-level statistics of such data
+    come from the GPU as well: same forest as the host passes and as the oracle's trainer."""
+    from oracle import random_forest_oracle as rfo
+
+    rng = np.random.default_rng(77)
+    n, d, nq = 4000, 24, 120
+    qid = np.sort(rng.integers(0, nq, n))
+    X = np.round(rng.normal(size=(n, d)), 3).astype(np.float32)
+    # labels on a fine dyadic grid (exact in the device's 2^-12 unit): candidate splits do not tie in
+    # importance, which is the one thing the reference leaves to an unspecified sort order
+    y = rng.integers(0, 4 * 4096, n) / 4096.0
+    lines = []
+    for i in range(n):
+        kind = rng.random()
+        if kind < 0.2:      # Sparse32: 3 ids, the largest >= 7
+            ids = sorted(set(int(v) for v in rng.integers(1, d + 1, 2)) | {int(rng.integers(7, d + 1))})
+        elif kind < 0.35:   # Dense32, shorter than the others
+            ids = list(range(1, int(rng.integers(d // 2, d)) + 1))
+        else:
+            ids = list(range(1, d + 1))
+        lines.append("%r qid:q%d %s" % (float(y[i]), qid[i], " ".join("%d:%s" % (f, repr(float(X[i, f - 1]))) for f in ids)))
+    path = tmp_path / "sparse_rows.libsvm"
+    path.write_text("\n".join(lines) + "\n")
+    ods = oracle.load_libsvm(str(path))
+    assert ods.present is not None and not ods.present.all()
+    params = {"feature_sampling_rate": 0.5, "instance_sampling_rate": 0.5, "max_depth": 6, "min_leaf_support": 3,
+              "num_trees": 6, "seed": 11, "split_candidates": 8, "split_method": "SquaredError"}
+    exp_spec = rfo.learn_forest(ods, params)
+    exp_scores = oracle.score_model(ods.X, exp_spec).tolist()
+    specs, counts = {}, {}
+    for where in ("host", "gpu"):
+        monkeypatch.setenv("FASTRANK_RF", where)
+        ds = fr.CDataset.open_ranksvm(str(path))
+        req = _rf_req(fr, **{k: v for k, v in params.items() if k != "split_method"})
+        before = int(fr.clib.lib.fr_dev_kernel_launches())
+        model = ds.train_model(req)
+        launched = int(fr.clib.lib.fr_dev_kernel_launches()) - before
+        specs[where] = model.to_dict()
+        counts[where] = launched
+        assert model.predict_dense(ds).tolist() == exp_scores, where
+    assert specs["host"] == specs["gpu"]
+    assert counts["gpu"] > counts["host"] + 20, counts  # the level statistics' kernels did run
+
+
 def test_concurrent_predict_and_evaluate_on_one_dataset(fr, oracle):
     """Predict shares the dataset's stream and score scratch with the evaluators: calls from several
     threads (cffi releases the GIL) with different models -- linear, forest, more models than the
