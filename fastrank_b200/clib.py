@@ -277,9 +277,16 @@ class CDataset(_Handle):
         request = json.dumps(fnums).encode("utf-8")
         return self._child(_take_result(lib.dataset_feature_sampling(self.pointer, request)))
 
-    def train_model(self, train_req: "TrainRequest") -> CModel:  # noqa: F821
+    def train_model(self, train_req: "TrainRequest", sweep: Optional[str] = None) -> CModel:  # noqa: F821
+        """The reference's train_model.  `sweep` (extension, coordinate ascent only): "exact" runs
+        the line searches on the exact-order kernel -- scores summed in the reference's feature
+        order, bit for bit -- instead of the batched sweep, whose scores add the varied coordinate's
+        term last and can differ in the last bits; "batched" / None is the default."""
         self._require_init()
-        request = ffi.new("char[]", json.dumps(train_req.to_dict()).encode("utf-8"))
+        req_dict = train_req.to_dict()
+        if sweep is not None:
+            req_dict["sweep"] = sweep
+        request = ffi.new("char[]", json.dumps(req_dict).encode("utf-8"))
         pointer = _take_result(lib.train_model(request, ffi.cast("void*", self.pointer)))
         return CModel(ffi.cast("CModel*", pointer), train_req)
 

@@ -260,6 +260,7 @@ const void *query_json(const void *json_cmd_str) {
             o.set("evals_computed", json::Value::uinteger(s.evals_computed));
             o.set("sweeps", json::Value::uinteger(s.sweeps));
             o.set("global_steps", json::Value::uinteger(s.global_steps));
+            o.set("sweep", json::Value::string(s.exact_sweep ? "exact" : "batched"));
             o.set("seconds_setup", json::Value::number(s.seconds_setup));
             o.set("seconds_device", json::Value::number(s.seconds_device));
             o.set("seconds_total", json::Value::number(s.seconds_total));
@@ -303,7 +304,12 @@ const CResult *train_model(void *train_request_json_ptr, void *dataset) {
             return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         };
         if (kind == "CoordinateAscent") {
-            const CoordinateAscentParams p = CoordinateAscentParams::from_json(params->obj[0].second);
+            CoordinateAscentParams p = CoordinateAscentParams::from_json(params->obj[0].second);
+            if (const json::Value *sweep = req.find("sweep")) {  // extension; absent in the reference's requests
+                if (sweep->kind != json::Value::String || (sweep->s != "exact" && sweep->s != "batched"))
+                    throw Error("invalid value for `sweep`: expected \"exact\" or \"batched\"");
+                p.exact_sweep = sweep->s == "exact";
+            }
             Evaluator ev(d.view, m, qrel.get());
             const double setup = seconds_since(t_begin);
             CModel *out = new CModel(coordinate_ascent_learn(p, d.view, ev, &stats));

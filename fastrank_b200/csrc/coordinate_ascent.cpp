@@ -138,6 +138,8 @@ Model coordinate_ascent_learn(const CoordinateAscentParams &p, const DatasetView
     bool use_fast = fr_dev_plan_has_fast_sweep(ev.plan()) != 0;
     if (const char *env = getenv("FASTRANK_SWEEP"))
         if (std::string(env) == "exact") use_fast = false;
+    if (p.exact_sweep) use_fast = false;  // asked for in the train request
+    stats.exact_sweep = !use_fast;
     bool speculate = use_fast && T > 0;
     if (const char *env = getenv("FASTRANK_SPECULATE")) speculate = speculate && atoi(env) != 0;
     const size_t stride = speculate ? 1 + 2 * T : 1 + T;

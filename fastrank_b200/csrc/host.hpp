@@ -231,6 +231,10 @@ struct CoordinateAscentParams {
     bool quiet = false;
     bool init_random = true;
     bool output_ensemble = false;
+    // not one of the reference's parameters (never serialised): TrainRequest's optional top-level
+    // "sweep": "exact" asks for the exact-order kernel (the reference's summation order, bit for bit)
+    // instead of the batched sweep
+    bool exact_sweep = false;
     static CoordinateAscentParams defaults();  // coordinate_ascent.rs:25-41
     static CoordinateAscentParams from_json(const json::Value &v);
     json::Value to_json() const;
@@ -257,6 +261,7 @@ struct TrainStats {
     uint64_t evals_computed = 0;  // candidates actually scored on the GPU (speculation included)
     uint64_t sweeps = 0;
     uint64_t global_steps = 0;
+    bool exact_sweep = false;     // the line searches ran on the exact-order kernel
     double seconds_setup = 0.0;   // evaluator construction: dataset upload (first use) + plan
     double seconds_device = 0.0;  // inside the fr_dev_* evaluation calls (copies, kernels, sync)
     double seconds_total = 0.0;   // the whole train_model call

@@ -479,7 +479,17 @@ def test_training_schedules_agree(fr, monkeypatch):
             monkeypatch.setenv(k, v)
         model = ds.train_model(req)
         stats = fr.query_json("last_train_stats")
+        assert stats["sweep"] == ("exact" if label == "exact" else "batched")
         results[label] = (model.to_dict()["Linear"]["weights"], stats["evals_consumed"], stats["global_steps"])
+    # the same choice through the API (an optional "sweep" key of the train request) instead of the environment
+    monkeypatch.delenv("FASTRANK_SWEEP", raising=False)
+    model = ds.train_model(req, sweep="exact")
+    stats = fr.query_json("last_train_stats")
+    assert stats["sweep"] == "exact"
+    results["exact_by_request"] = (model.to_dict()["Linear"]["weights"], stats["evals_consumed"], stats["global_steps"])
+    assert results["exact_by_request"] == results["exact"]
+    with pytest.raises(Exception, match="sweep"):
+        ds.train_model(req, sweep="fastest")
     base = results["no_speculation"]
     for label in ("default", "no_lookahead", "exact"):
         assert results[label][0] == base[0], label
