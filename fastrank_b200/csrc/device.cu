@@ -826,7 +826,10 @@ int launch_batch(fr_dev_plan *pl, int kc, int tb, const BatchArgs &args_in, cuda
     BatchArgs args = args_in;
     args.wchunk = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(args.dm, 1),
                                                            32768u / (uint32_t)(kc * sizeof(double))));
-    const size_t smem = eval_smem_bytes(kc, tb) + (size_t)args.wchunk * kc * sizeof(double);
+    // + 8 features of slack: the unrolled tail of the feature loop reads weights in 16-byte pairs,
+    // and the compiler may fetch the pair of a feature that is then not used (found by memcheck with
+    // a one-feature model: an 8-byte read past the staging area)
+    const size_t smem = eval_smem_bytes(kc, tb) + ((size_t)args.wchunk + 8) * kc * sizeof(double);
     PlanView pv = pl->view();
     if (kc == 1 && tb == 128) {  // a single weight vector: the HBM-bound case gets its own instance
         uint32_t gx = 1;
