@@ -10,6 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+OTHER_MEASURES = (("mrr", 2), ("map", 1), ("ndcg", 0))
+
+
 def workload():
     from tests.helpers import synth
 
@@ -91,6 +94,13 @@ def main():
     mbase, mfids, mcands = many_rows()
     many = plan.coord_sweeps(mbase, mfids, mcands, fast=True)
     nq_global = int(lib.fr_dev_plan_global_queries(plan.ptr))
+    # the measures served by the slot mode of the packed kernel (and RR's one-rank path) reduce
+    # through the same kernel tail
+    others = {}
+    for name, metric in OTHER_MEASURES:
+        p2 = dev.plan(metric, -1)
+        assert lib.fr_dev_plan_set_comm(p2.ptr, comm.ptr) == 0
+        others[name] = p2.coord_sweeps(base, fids, cands, fast=True).tolist()
     dev.close()
     # the reference-compatible surface on a shard: train_model sees all-reduced means
     ds = fr.CDataset.from_numpy(Xl, yl, ql)
@@ -110,7 +120,7 @@ def main():
                                             np.ascontiguousarray(q2[rows2]))
     gathered = [None] * world
     dist.all_gather_object(gathered, (fast.tolist(), exact.tolist(), lin.tolist(), nq_global, weights, mean,
-                                      many.tolist(), long_lists))
+                                      many.tolist(), long_lists, others))
     if rank == 0:
         with open(out_path, "w") as fp:
             json.dump({"world": world, "ranks": gathered}, fp)

@@ -26,7 +26,7 @@ def test_two_ranks_match_one_gpu(tmp_path):
     import fastrank_b200 as fr
     from fastrank_b200._native import lib
     from fastrank_b200.kernels import DevDataset, dense_query_index
-    from tests.dist_gpu_worker import long_list_data, many_rows, train_long_lists, workload
+    from tests.dist_gpu_worker import OTHER_MEASURES, long_list_data, many_rows, train_long_lists, workload
 
     if lib.fr_dev_device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -48,6 +48,8 @@ def test_two_ranks_match_one_gpu(tmp_path):
         lin, _ = plan.eval_linear(W, per_query=False)
         mbase, mfids, mcands = many_rows()
         many = plan.coord_sweeps(mbase, mfids, mcands, fast=True)
+        others = {name: dev.plan(metric, -1).coord_sweeps(base, fids, cands, fast=True).tolist()
+                  for name, metric in OTHER_MEASURES}
     finally:
         dev.close()
     ds = fr.CDataset.from_numpy(X, y, qid)
@@ -58,7 +60,8 @@ def test_two_ranks_match_one_gpu(tmp_path):
     req.params.quiet = True
     model = ds.train_model(req)
     long_lists = {kind: train_long_lists(fr, *long_list_data(kind)) for kind in ("hybrid", "mixed")}
-    for r_fast, r_exact, r_lin, nq_global, weights, mean, r_many, r_long in got["ranks"]:
+    for r_fast, r_exact, r_lin, nq_global, weights, mean, r_many, r_long, r_others in got["ranks"]:
+        assert r_others == others   # MRR / MAP / NDCG without cut-off: slot mode + the fused reduction
         for kind in ("hybrid", "mixed"):   # lists too long for a sweep tile, evenly and unevenly sharded
             assert r_long[kind][0] == long_lists[kind][0], kind
             assert r_long[kind][1] == long_lists[kind][1], kind
